@@ -1,0 +1,156 @@
+/*
+ * pcb_b200.h -- C ABI of the B200-native batch-evaluation engine for PyChebyshev interpolants.
+ *
+ * The reference (0xC000005/PyChebyshev v0.21.1) has no FFI seam: its evaluation path is the
+ * Python method surface of ChebyshevApproximation / ChebyshevTT / ChebyshevSpline /
+ * ChebyshevSlider.  Each entry point below replaces the *body* of one of those methods; the
+ * reference lines are cited per function (paths relative to src/pychebyshev/ of the reference).
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add per method.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  All floating point is IEEE fp64.
+ *   - "plan" = immutable device-resident copy of one interpolant on one GPU, created from HOST
+ *     arrays (the Python object's NumPy arrays) and destroyed with pcb_plan_destroy.
+ *   - d_* arguments are DEVICE pointers owned by the caller (PyTorch allocations), `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  Evaluation calls are
+ *     asynchronous on `stream`, never allocate, and are re-entrant across streams.
+ *   - points are (N, D) row-major fp64 in the USER dimension order; outputs are (N, G) row-major.
+ *   - return 0 on success, a negative PCB_E* code otherwise; pcb_last_error() returns a
+ *     thread-local message for the most recent failure on the calling thread.
+ */
+#ifndef PCB_B200_H
+#define PCB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PCB_API __attribute__((visibility("default")))
+#else
+#define PCB_API
+#endif
+
+#define PCB_OK 0
+#define PCB_EINVAL (-1)   /* bad argument (maps to ValueError)            */
+#define PCB_ECUDA (-2)    /* CUDA runtime failure (maps to RuntimeError)  */
+#define PCB_ENOMEM (-3)   /* allocation failure                           */
+#define PCB_EUNSUPPORTED (-4) /* shape outside what the kernels cover (maps to NotImplementedError) */
+
+#define PCB_MAX_DIMS 32
+
+PCB_API int pcb_version(void);
+PCB_API const char *pcb_last_error(void);
+PCB_API int pcb_device_count(void);
+/* sm count, max opt-in shared memory per block, compute capability major*10+minor */
+PCB_API int pcb_device_info(int dev, int *sm_count, int *smem_optin, int *cc);
+PCB_API int pcb_plan_destroy(void *plan);
+
+/* ---------------------------------------------------------------------------------------------
+ * ChebyshevTT   (tensor_train.py)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Build a device plan from coefficient cores.
+ *   n[k], lo[k], hi[k]  : storage-frame node counts / domain (ChebyshevTT.n_nodes, .domain)
+ *   ranks[0..D]         : TT ranks, ranks[0] = ranks[D] = 1 (ChebyshevTT.tt_ranks)
+ *   dim_order[k]        : user column stored at TT position k (ChebyshevTT._dim_order)
+ *   cores_cat           : _coeff_cores[k] (r_{k-1}, n_k, r_k) C-order, concatenated
+ */
+PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, const int32_t *ranks, const double *lo,
+                       const double *hi, const int32_t *dim_order, const double *cores_cat,
+                       void **plan);
+
+/* Replaces ChebyshevTT.eval_batch (tensor_train.py:2217-2265): d_out[i] = value at point i. */
+PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream);
+
+/* Replaces a loop of ChebyshevTT.eval_multi over points (tensor_train.py:2267-2463): value and
+ * central finite differences with h = (b-a)*1e-4 and the boundary nudge, G derivative-order
+ * rows (user frame, G x D int32, HOST pointer) -> d_out (N, G).  Orders > 2 -> PCB_EINVAL
+ * ("Derivative order k not supported (use 1 or 2)").  `algo`: 0 = auto, 1 = one chain per stencil
+ * point (any orders, <= 3 active dims per row), 2 = shared left/right partial products (rows with
+ * <= 1 active dim). */
+PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G, const int32_t *orders,
+                   double *d_out, int algo, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ChebyshevApproximation   (barycentric.py)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Build a device plan for G pre-differentiated tensors of one interpolant.
+ *   n[d]                 : ChebyshevApproximation.n_nodes
+ *   nodes_cat/weights_cat: .nodes[d] / .weights[d] concatenated over d
+ *   tensors_host[g]      : C-order tensor after _apply_derivative_passes(tensor_values, order_g)
+ *                          (barycentric.py:951-990; made on the host with the reference's recipe)
+ */
+PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, const double *nodes_cat,
+                         const double *weights_cat, int G, const double *const *tensors_host,
+                         void **plan);
+
+/* Replaces G calls of ChebyshevApproximation.vectorized_eval_batch (barycentric.py:992-1047),
+ * one per pre-differentiated tensor: d_out (N, G).  `algo`: 0 = auto, 1 = thread-per-query FMA
+ * evaluator, 2 = DMMA mode-1 GEMM with fused tail (D >= 3). */
+PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t N, double *d_out, int algo,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ChebyshevSpline   (spline.py)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Build a device plan for a spline with P = prod(num_knots[d] + 1) pieces (C-order).
+ *   piece_n            : P x D node counts (nested n_nodes allowed)
+ *   piece_nodes_cat    : for piece p, for dim d: nodes (piece_n[p][d] doubles), concatenated
+ *   piece_weights_cat  : same layout, barycentric weights
+ *   piece_tensors_host : P x G pointers, piece-major; each a C-order pre-differentiated tensor
+ */
+PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num_knots, const double *knots_cat, int P,
+                           const int32_t *piece_n, const double *piece_nodes_cat,
+                           const double *piece_weights_cat, int G,
+                           const double *const *piece_tensors_host, void **plan);
+
+/* Replaces the routing lines of ChebyshevSpline.eval_batch (spline.py:677-690; single-point twin
+ * _find_piece :414-445): d_piece[i] = C-order flat piece index, bit-exact integer work. */
+PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int64_t N, int32_t *d_piece, void *stream);
+
+/* Replaces ChebyshevSpline.eval_batch (spline.py:633-700) for G derivative tensors: d_out (N, G).
+ * d_piece may be NULL (lookup fused) or receive the piece indices. */
+PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64_t N, double *d_out, int32_t *d_piece,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ChebyshevSlider   (slider.py)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Build a device plan for an additive slider.
+ *   S slides; group_size[s] dims each; group_dims_cat = partition flattened
+ *   slide_n_cat / slide_nodes_cat / slide_weights_cat : per slide, per group dim
+ *   G outputs; out_slide[g] = -1 -> value row: pivot + sum_s (slide_s - pivot) (slider.py:310-318)
+ *                           = -2 -> cross-slide mixed partial: exactly 0.0      (slider.py:297-298)
+ *                           = s  -> derivative owned by slide s                  (slider.py:301-307)
+ *   slide_tensors_host : G x S pointers (row g, slide s); only the entries a row uses are read
+ */
+PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32_t *group_size,
+                           const int32_t *group_dims_cat, const int32_t *slide_n_cat,
+                           const double *slide_nodes_cat, const double *slide_weights_cat,
+                           double pivot_value, int G, const int32_t *out_slide,
+                           const double *const *slide_tensors_host, void **plan);
+
+/* Replaces a loop of ChebyshevSlider.eval over points (slider.py:247-318): d_out (N, G). */
+PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Roofline probes (bench.py): measured FP64 pipe peaks of the device, in TFLOP/s.
+ *   kind 0 = DFMA (register-resident FMA chains), 1 = DMMA (mma.sync m8n8k4 f64)
+ * ------------------------------------------------------------------------------------------ */
+PCB_API int pcb_probe_fp64_peak(int dev, int kind, double *tflops, double *ms);
+
+/* Number of kernels this library has launched on the calling process (bench.py gpu_launches). */
+PCB_API int64_t pcb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCB_B200_H */

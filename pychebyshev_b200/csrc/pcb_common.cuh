@@ -1,0 +1,65 @@
+// Shared host/device helpers of libpcb_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pcb_b200.h"
+
+namespace pcb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+extern std::atomic<int64_t> g_launches;
+
+int fail(int code, const char *fmt, ...);
+
+#define PCB_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return pcb::fail(PCB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define PCB_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) return pcb::fail(PCB_EINVAL, __VA_ARGS__);  \
+    } while (0)
+
+// ---- plans ------------------------------------------------------------------------------------
+enum PlanKind : int { PLAN_TT = 0x7454, PLAN_FULL = 0x4655, PLAN_SPLINE = 0x5350, PLAN_SLIDER = 0x534c };
+
+struct PlanBase {
+    int kind;
+    int dev;
+    int sm_count;
+    int smem_optin;
+    virtual ~PlanBase() {}
+};
+
+int device_props(int dev, int *sm_count, int *smem_optin, int *cc);
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// RAII device switch: evaluation calls must not change the caller's current device.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace pcb

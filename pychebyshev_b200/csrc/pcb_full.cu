@@ -1,0 +1,553 @@
+// ChebyshevApproximation batch evaluation on sm_100a.
+//
+// Replaces ChebyshevApproximation.vectorized_eval_batch (reference barycentric.py:992-1047) for G
+// pre-differentiated tensors at once (the derivative passes of barycentric.py:951-990 are applied
+// on the host with the reference's own recipe and uploaded; SURVEY.md finding 2).
+//
+// Two kernels:
+//   full_fma_kernel   thread-per-query depth-first FMA evaluator (any D <= 8; small tensors)
+//   full_dmma_kernel  mode-1 contraction as an FP64 tensor-core GEMM (mma.sync m8n8k4 -> DMMA.8x8x4)
+//                     with the remaining mode contractions fused on chip:
+//                       M = 8 queries per MMA tile, K = last tensor axis (4 per k-step),
+//                       N = 8 positions of the flattened leading axes; the two axes in between are
+//                       folded with per-query weights into register accumulators; the leading
+//                       axes are folded at the end of each 8-column group and the four lanes of a
+//                       quad are reduced with warp shuffles.  The prepared tensor is streamed
+//                       through shared memory with bulk async copies (TMA, cp.async.bulk) behind
+//                       an mbarrier full/empty ring fed by a dedicated producer warp.
+#include "pcb_grid.cuh"
+
+namespace pcb {
+
+constexpr int FULL_FMA_THREADS = 128;
+
+constexpr int DM_WARPS = 8;                       // consumer warps per CTA
+constexpr int DM_MT = 4;                          // 8-query MMA row tiles per warp
+constexpr int DM_QT = DM_WARPS * DM_MT * 8;       // queries per CTA tile (256)
+constexpr int DM_THREADS = (DM_WARPS + 1) * 32;   // + 1 producer warp
+constexpr int DM_MAX_KB = 8;                      // last axis up to 32 nodes
+constexpr int DM_MAX_STAGES = 4;
+
+struct DmmaParams {
+    int D;
+    int G;
+    int n[PCB_MAX_DIMS];
+    int woff[PCB_MAX_DIMS];  // offset of dim d's weight rows in the smem weight table (rows)
+    int n_lead_dims;         // dims [0, n_lead_dims) are flattened into the MMA column axis
+    int L;                   // prod n[lead dims]
+    int LG;                  // ceil(L / 8)
+    int nc, nd;              // extents of the two middle axes (1 when absent)
+    int dim_c, dim_d;        // their dim indices (-1 when absent)
+    int KB;                  // ceil(n_last / 4)
+    int wrows;               // rows of the smem weight table (sum of n over dims < D-1)
+    int slab;                // doubles per (lead group, c) slab = nd * KB * 32
+    int stages;
+    long long gstride;       // doubles per prepared tensor
+    int node_off[PCB_MAX_DIMS];
+};
+
+struct FullPlan : PlanBase {
+    GridDesc gd;
+    int G = 0;
+    double *d_nodes = nullptr;    // nodes then weights, dims concatenated
+    double *d_weights = nullptr;
+    double *d_tensors = nullptr;  // G C-order tensors
+    double *d_prepared = nullptr; // G prepared (fragment-ordered, zero-padded) tensors
+    bool dmma_ok = false;
+    DmmaParams dm;
+    size_t dm_smem = 0;
+    ~FullPlan() override {
+        if (d_nodes) cudaFree(d_nodes);
+        if (d_tensors) cudaFree(d_tensors);
+        if (d_prepared) cudaFree(d_prepared);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FMA evaluator
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(FULL_FMA_THREADS)
+full_fma_kernel(const __grid_constant__ GridDesc gd, int G, const double *__restrict__ nodes,
+                const double *__restrict__ weights, const double *__restrict__ tensors,
+                const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    double *ws = smem + threadIdx.x;
+    const int stride = blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        int off = 0;
+        for (int d = 0; d < gd.D; ++d) {
+            grid_weight_row(__ldg(pts + q * gd.D + d), gd.n[d], nodes + gd.node_off + off,
+                            weights + gd.node_off + off, ws + (size_t)off * stride, stride);
+            off += gd.n[d];
+        }
+        for (int g = 0; g < G; ++g)
+            out[q * G + g] = grid_contract(gd, tensors + gd.tensor_off + g * gd.size, ws, stride);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DMMA kernel
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor core (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct DmmaSmem {
+    int w;      // weight table [wrows][DM_QT]
+    int ring;   // stages * slab doubles (also scratch for the last-axis weights in the prologue)
+    int bars;   // 2 * stages uint64
+    int total;  // doubles
+};
+
+__host__ __device__ inline DmmaSmem dmma_smem_layout(const DmmaParams &P) {
+    DmmaSmem L;
+    L.w = 0;
+    L.ring = L.w + P.wrows * DM_QT;
+    int ring = P.stages * P.slab;
+    const int scratch = P.KB * 4 * DM_QT;  // last-axis weight rows, padded to KB*4
+    if (ring < scratch) ring = scratch;
+    L.bars = L.ring + ring;
+    L.total = L.bars + 2 * DM_MAX_STAGES;
+    return L;
+}
+
+template <int KB>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+full_dmma_kernel(const __grid_constant__ DmmaParams P, const double *__restrict__ nodes,
+                 const double *__restrict__ weights, const double *__restrict__ prepared,
+                 const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
+    extern __shared__ __align__(128) double smem[];
+    const DmmaSmem L = dmma_smem_layout(P);
+    double *w_s = smem + L.w;
+    double *ring = smem + L.ring;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint64_t *empty = full + DM_MAX_STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int D = P.D;
+    const int nlast = P.n[D - 1];
+    const int64_t ntiles = (N + DM_QT - 1) / DM_QT;
+    const uint32_t slab_bytes = (uint32_t)P.slab * 8u;
+    const int slabs_per_g = P.LG * P.nc;
+
+    if (tid == 0) {
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], DM_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ring position persists across tiles (producer and consumers advance in lock step)
+    uint32_t it = 0;  // slabs handled so far by this thread's role
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t q0 = tile * DM_QT;
+        // ---- prologue: barycentric weight rows of the tile's queries (K-A0) -----------------
+        // one (query, dim) pair per thread iteration; reference barycentric.py:1038-1045
+        __syncthreads();  // every warp finished the previous tile (ring drained, w_s free)
+        for (int e = tid; e < DM_QT * D; e += DM_THREADS) {
+            const int ql = e % DM_QT;
+            const int d = e / DM_QT;
+            int64_t q = q0 + ql;
+            if (q >= N) q = N - 1;
+            const double x = __ldg(pts + q * D + d);
+            const int n = P.n[d];
+            double *dst;
+            int rows;
+            if (d == D - 1) {
+                dst = ring + ql;
+                rows = KB * 4;
+            } else {
+                dst = w_s + (size_t)P.woff[d] * DM_QT + ql;
+                rows = n;
+            }
+            grid_weight_row(x, n, nodes + P.node_off[d], weights + P.node_off[d], dst, DM_QT);
+            for (int i = n; i < rows; ++i) dst[i * DM_QT] = 0.0;
+        }
+        __syncthreads();
+
+        if (warp == DM_WARPS) {
+            // ---- producer warp: stream the prepared tensors through the ring ------------------
+            __syncthreads();  // matches the consumers' "A fragments loaded" barrier
+            if (lane == 0) {
+                for (int g = 0; g < P.G; ++g) {
+                    const double *src = prepared + (size_t)g * P.gstride;
+                    for (int sidx = 0; sidx < slabs_per_g; ++sidx, ++it) {
+                        const int s = it % P.stages;
+                        const uint32_t round = it / P.stages;
+                        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+                        mbar_arrive_expect_tx(&full[s], slab_bytes);
+                        bulk_g2s(ring + (size_t)s * P.slab, src + (size_t)sidx * P.slab, slab_bytes,
+                                 &full[s]);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ---- consumer warps ---------------------------------------------------------------
+            const int qrow = warp * (DM_MT * 8) + (lane >> 2);  // + mt*8: this lane's MMA row
+            const int kcol = lane & 3;
+            double afrag[KB][DM_MT];
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int mt = 0; mt < DM_MT; ++mt)
+                    afrag[kb][mt] = ring[(size_t)(kb * 4 + kcol) * DM_QT + qrow + mt * 8];
+            __syncthreads();  // scratch consumed: the producer may overwrite the ring
+
+            for (int g = 0; g < P.G; ++g) {
+                double outacc[DM_MT];
+#pragma unroll
+                for (int mt = 0; mt < DM_MT; ++mt) outacc[mt] = 0.0;
+                for (int lg = 0; lg < P.LG; ++lg) {
+                    double acc3[DM_MT][2];
+#pragma unroll
+                    for (int mt = 0; mt < DM_MT; ++mt) acc3[mt][0] = acc3[mt][1] = 0.0;
+                    for (int c = 0; c < P.nc; ++c, ++it) {
+                        const int s = it % P.stages;
+                        mbar_wait(&full[s], (it / P.stages) & 1);
+                        const double *slab = ring + (size_t)s * P.slab + lane;
+                        double acc2[DM_MT][2];
+#pragma unroll
+                        for (int mt = 0; mt < DM_MT; ++mt) acc2[mt][0] = acc2[mt][1] = 0.0;
+                        for (int d = 0; d < P.nd; ++d) {
+                            double cf[DM_MT][2];
+#pragma unroll
+                            for (int mt = 0; mt < DM_MT; ++mt) cf[mt][0] = cf[mt][1] = 0.0;
+#pragma unroll
+                            for (int kb = 0; kb < KB; ++kb) {
+                                const double b = slab[(d * KB + kb) * 32];
+#pragma unroll
+                                for (int mt = 0; mt < DM_MT; ++mt)
+                                    dmma884(cf[mt][0], cf[mt][1], afrag[kb][mt], b);
+                            }
+                            if (P.dim_d >= 0) {
+                                const double *wd = w_s + (size_t)(P.woff[P.dim_d] + d) * DM_QT + qrow;
+#pragma unroll
+                                for (int mt = 0; mt < DM_MT; ++mt) {
+                                    const double w = wd[mt * 8];
+                                    acc2[mt][0] = fma(w, cf[mt][0], acc2[mt][0]);
+                                    acc2[mt][1] = fma(w, cf[mt][1], acc2[mt][1]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int mt = 0; mt < DM_MT; ++mt) {
+                                    acc2[mt][0] = cf[mt][0];
+                                    acc2[mt][1] = cf[mt][1];
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[s]);  // slab consumed by this warp
+                        if (P.dim_c >= 0) {
+                            const double *wc = w_s + (size_t)(P.woff[P.dim_c] + c) * DM_QT + qrow;
+#pragma unroll
+                            for (int mt = 0; mt < DM_MT; ++mt) {
+                                const double w = wc[mt * 8];
+                                acc3[mt][0] = fma(w, acc2[mt][0], acc3[mt][0]);
+                                acc3[mt][1] = fma(w, acc2[mt][1], acc3[mt][1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int mt = 0; mt < DM_MT; ++mt) {
+                                acc3[mt][0] = acc2[mt][0];
+                                acc3[mt][1] = acc2[mt][1];
+                            }
+                        }
+                    }
+                    // fold the leading axes: this lane owns columns p0, p0 + 1 of the group
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int p = lg * 8 + kcol * 2 + e;
+                        if (p < P.L) {
+#pragma unroll
+                            for (int mt = 0; mt < DM_MT; ++mt) {
+                                double wl = 1.0;
+                                int rem = p;
+                                for (int dd = P.n_lead_dims - 1; dd >= 0; --dd) {
+                                    const int idx = rem % P.n[dd];
+                                    rem /= P.n[dd];
+                                    wl *= w_s[(size_t)(P.woff[dd] + idx) * DM_QT + qrow + mt * 8];
+                                }
+                                outacc[mt] = fma(wl, acc3[mt][e], outacc[mt]);
+                            }
+                        }
+                    }
+                }
+                // reduce the four lanes of each quad (they hold different columns of one query)
+#pragma unroll
+                for (int mt = 0; mt < DM_MT; ++mt) {
+                    double v = outacc[mt];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int64_t q = q0 + qrow + mt * 8;
+                    if (kcol == 0 && q < N) out[q * P.G + g] = v;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+// Reorder one C-order tensor into MMA B-fragment order:
+//   prepared[((lg * nc + c) * nd + d) * KB + kb][lane] = T[lead = 8 lg + lane/4][c][d][e = 4 kb + lane%4]
+static void dmma_prepare(const DmmaParams &P, const double *t, double *dst) {
+    const int nlast = P.n[P.D - 1];
+    const long long s_d = nlast;
+    const long long s_c = s_d * P.nd;
+    const long long s_lead = s_c * P.nc;
+    size_t o = 0;
+    for (int lg = 0; lg < P.LG; ++lg)
+        for (int c = 0; c < P.nc; ++c)
+            for (int d = 0; d < P.nd; ++d)
+                for (int kb = 0; kb < P.KB; ++kb)
+                    for (int lane = 0; lane < 32; ++lane, ++o) {
+                        const int lead = lg * 8 + lane / 4;
+                        const int e = kb * 4 + lane % 4;
+                        dst[o] = (lead < P.L && e < nlast)
+                                     ? t[lead * s_lead + c * s_c + d * s_d + e]
+                                     : 0.0;
+                    }
+}
+
+static bool dmma_configure(FullPlan *pl, const int32_t *n) {
+    const int D = pl->gd.D;
+    if (D < 2) return false;
+    DmmaParams &P = pl->dm;
+    memset(&P, 0, sizeof(P));
+    P.D = D;
+    P.G = pl->G;
+    int off = 0, woff = 0;
+    for (int d = 0; d < D; ++d) {
+        P.n[d] = n[d];
+        P.node_off[d] = off;
+        off += n[d];
+        P.woff[d] = woff;
+        if (d < D - 1) woff += n[d];
+    }
+    P.wrows = woff;
+    P.KB = (n[D - 1] + 3) / 4;
+    if (P.KB > DM_MAX_KB) return false;
+    // number of middle axes: as many as possible (<= 2) while the flattened leading axes still
+    // fill the 8-wide MMA column tiles well
+    int best_m = -1;
+    double best_eff = -1.0;
+    for (int m = (D - 2 < 2 ? D - 2 : 2); m >= 0; --m) {
+        long long L = 1;
+        for (int d = 0; d < D - 1 - m; ++d) L *= n[d];
+        const double eff = (double)L / (double)(((L + 7) / 8) * 8);
+        if (eff >= 0.9) {  // deepest nesting whose column tiles are at least 90 % full
+            best_m = m;
+            break;
+        }
+        if (eff > best_eff) {
+            best_eff = eff;
+            best_m = m;
+        }
+    }
+    const int m = best_m;
+    P.n_lead_dims = D - 1 - m;
+    long long L = 1;
+    for (int d = 0; d < P.n_lead_dims; ++d) L *= n[d];
+    if (L > (1 << 28)) return false;
+    P.L = (int)L;
+    P.LG = (P.L + 7) / 8;
+    P.dim_d = m >= 1 ? D - 2 : -1;
+    P.dim_c = m >= 2 ? D - 3 : -1;
+    P.nd = P.dim_d >= 0 ? n[P.dim_d] : 1;
+    P.nc = P.dim_c >= 0 ? n[P.dim_c] : 1;
+    P.slab = P.nd * P.KB * 32;
+    P.gstride = (long long)P.LG * P.nc * P.slab;
+    // stages: as many as fit (<= 4)
+    for (int st = DM_MAX_STAGES; st >= 2; --st) {
+        P.stages = st;
+        const DmmaSmem Ls = dmma_smem_layout(P);
+        if ((size_t)Ls.total * 8 <= (size_t)pl->smem_optin) {
+            pl->dm_smem = (size_t)Ls.total * 8;
+            return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace pcb
+
+using namespace pcb;
+
+extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, const double *nodes_cat,
+                                    const double *weights_cat, int G,
+                                    const double *const *tensors_host, void **plan) {
+    PCB_REQUIRE(plan && n && nodes_cat && weights_cat && tensors_host, "null argument");
+    PCB_REQUIRE(D >= 1 && D <= GRID_MAXD, "num_dimensions %d outside [1, %d]", D, GRID_MAXD);
+    PCB_REQUIRE(G >= 1 && G <= 64, "number of derivative tensors %d outside [1, 64]", G);
+    FullPlan *pl = new FullPlan();
+    pl->kind = PLAN_FULL;
+    pl->dev = dev;
+    pl->G = G;
+    int cc = 0;
+    if (int rc = device_props(dev, &pl->sm_count, &pl->smem_optin, &cc)) {
+        delete pl;
+        return rc;
+    }
+    GridDesc &gd = pl->gd;
+    memset(&gd, 0, sizeof(gd));
+    gd.D = D;
+    gd.size = 1;
+    for (int d = 0; d < D; ++d) {
+        if (n[d] < 1) {
+            delete pl;
+            return fail(PCB_EINVAL, "n_nodes[%d] must be >= 1", d);
+        }
+        gd.n[d] = n[d];
+        gd.sum_n += n[d];
+        gd.size *= n[d];
+    }
+    DeviceGuard guard(dev);
+    const size_t nb = (size_t)gd.sum_n * sizeof(double);
+    const size_t tb = (size_t)gd.size * sizeof(double);
+    if (!guard.ok || cudaMalloc(&pl->d_nodes, 2 * nb) != cudaSuccess ||
+        cudaMalloc(&pl->d_tensors, tb * G) != cudaSuccess) {
+        delete pl;
+        return fail(PCB_ENOMEM, "device allocation for the full-tensor plan failed");
+    }
+    pl->d_weights = pl->d_nodes + gd.sum_n;
+    bool ok = cudaMemcpy(pl->d_nodes, nodes_cat, nb, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(pl->d_weights, weights_cat, nb, cudaMemcpyHostToDevice) == cudaSuccess;
+    for (int g = 0; ok && g < G; ++g)
+        ok = cudaMemcpy(pl->d_tensors + (size_t)g * gd.size, tensors_host[g], tb,
+                        cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        delete pl;
+        return fail(PCB_ECUDA, "upload of the full-tensor plan failed");
+    }
+    // tensor-core path: prepared copies in fragment order
+    pl->dmma_ok = dmma_configure(pl, n);
+    if (pl->dmma_ok) {
+        const size_t pb = (size_t)pl->dm.gstride * sizeof(double);
+        if (cudaMalloc(&pl->d_prepared, pb * G) != cudaSuccess) {
+            cudaGetLastError();
+            pl->dmma_ok = false;
+        } else {
+            std::vector<double> buf((size_t)pl->dm.gstride);
+            for (int g = 0; ok && g < G; ++g) {
+                dmma_prepare(pl->dm, tensors_host[g], buf.data());
+                ok = cudaMemcpy(pl->d_prepared + (size_t)g * pl->dm.gstride, buf.data(), pb,
+                                cudaMemcpyHostToDevice) == cudaSuccess;
+            }
+            if (!ok) {
+                delete pl;
+                return fail(PCB_ECUDA, "upload of the prepared tensors failed");
+            }
+        }
+    }
+    *plan = pl;
+    return PCB_OK;
+}
+
+template <int KB>
+static int launch_dmma(FullPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+    PCB_CUDA(cudaFuncSetAttribute(full_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl->dm_smem));
+    const int64_t ntiles = (N + DM_QT - 1) / DM_QT;
+    const int grid = (int)(ntiles < pl->sm_count ? ntiles : pl->sm_count);
+    full_dmma_kernel<KB><<<grid, DM_THREADS, pl->dm_smem, st>>>(pl->dm, pl->d_nodes, pl->d_weights,
+                                                              pl->d_prepared, d_points, N, d_out);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}
+
+extern "C" PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t N, double *d_out, int algo,
+                             void *stream) {
+    FullPlan *pl = static_cast<FullPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_FULL, "not a full-tensor plan");
+    PCB_REQUIRE(N >= 0, "negative N");
+    PCB_REQUIRE(algo >= 0 && algo <= 2, "algo %d not available", algo);
+    if (N == 0) return PCB_OK;
+    PCB_REQUIRE(d_points && d_out, "null device pointer");
+    DeviceGuard guard(pl->dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (algo == 2 && !pl->dmma_ok)
+        return fail(PCB_EUNSUPPORTED, "tensor-core path not available for this shape");
+    // auto: the tensor-core GEMM once the tensor is big enough to amortise a 256-query tile
+    const bool use_dmma = algo == 2 || (algo == 0 && pl->dmma_ok && pl->gd.size >= 4096 && N >= 64);
+    if (use_dmma) {
+        switch (pl->dm.KB) {
+            case 1: return launch_dmma<1>(pl, d_points, N, d_out, st);
+            case 2: return launch_dmma<2>(pl, d_points, N, d_out, st);
+            case 3: return launch_dmma<3>(pl, d_points, N, d_out, st);
+            case 4: return launch_dmma<4>(pl, d_points, N, d_out, st);
+            case 5: return launch_dmma<5>(pl, d_points, N, d_out, st);
+            case 6: return launch_dmma<6>(pl, d_points, N, d_out, st);
+            case 7: return launch_dmma<7>(pl, d_points, N, d_out, st);
+            case 8: return launch_dmma<8>(pl, d_points, N, d_out, st);
+            default:
+                if (algo == 2)
+                    return fail(PCB_EUNSUPPORTED, "last axis with %d nodes exceeds the register "
+                                "budget of the tensor-core path", pl->gd.n[pl->gd.D - 1]);
+        }
+    }
+    const size_t smem = (size_t)pl->gd.sum_n * FULL_FMA_THREADS * sizeof(double);
+    if (smem > (size_t)pl->smem_optin)
+        return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory",
+                    pl->gd.sum_n);
+    PCB_CUDA(cudaFuncSetAttribute(full_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, full_fma_kernel, FULL_FMA_THREADS, smem));
+    const int64_t want = (N + FULL_FMA_THREADS - 1) / FULL_FMA_THREADS;
+    const int64_t cap = (int64_t)pl->sm_count * (per_sm > 0 ? per_sm : 1);
+    const int grid = (int)(want < cap ? want : cap);
+    full_fma_kernel<<<grid, FULL_FMA_THREADS, smem, st>>>(pl->gd, pl->G, pl->d_nodes, pl->d_weights,
+                                                         pl->d_tensors, d_points, N, d_out);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}

@@ -1,0 +1,391 @@
+// ChebyshevSpline (piece lookup + per-piece evaluation) and ChebyshevSlider (additive slides).
+//
+// Spline: replaces ChebyshevSpline.eval_batch (reference spline.py:633-700).  The routing
+//   (spline.py:677-690) is integer work and bit-exact; the per-piece evaluation is the
+//   thread-per-query barycentric evaluator of pcb_grid.cuh on the piece's own nodes/weights.
+//   The reference groups points by piece and calls the piece evaluator per group; on the device
+//   every query simply indexes its piece's descriptor, so no bucketing pass is needed.
+// Slider: replaces a loop of ChebyshevSlider.eval (reference slider.py:247-318).
+#include "pcb_grid.cuh"
+
+namespace pcb {
+
+constexpr int PW_THREADS = 128;
+
+struct SplinePlan : PlanBase {
+    int D = 0, P = 0, G = 0;
+    int max_sum_n = 0;
+    int *d_num_knots = nullptr;  // [D] then knot_off [D]
+    int *d_knot_off = nullptr;
+    double *d_knots = nullptr;
+    GridDesc *d_desc = nullptr;  // [P]
+    double *d_nodes = nullptr;   // all pieces: nodes then weights (same offsets)
+    double *d_weights = nullptr;
+    double *d_tensors = nullptr;
+    ~SplinePlan() override {
+        if (d_num_knots) cudaFree(d_num_knots);
+        if (d_knots) cudaFree(d_knots);
+        if (d_desc) cudaFree(d_desc);
+        if (d_nodes) cudaFree(d_nodes);
+        if (d_tensors) cudaFree(d_tensors);
+    }
+};
+
+struct SliderPlan : PlanBase {
+    int D = 0, S = 0, G = 0;
+    int max_sum_n = 0;
+    double pivot = 0.0;
+    GridDesc *d_desc = nullptr;      // [S]; tensor_off unused (see d_tensor_off)
+    int *d_group_off = nullptr;      // [S+1] then group dims, then out_slide [G]
+    int *d_group_dims = nullptr;
+    int *d_out_slide = nullptr;
+    long long *d_tensor_off = nullptr;  // [G][S], -1 when unused
+    double *d_nodes = nullptr;
+    double *d_weights = nullptr;
+    double *d_tensors = nullptr;
+    ~SliderPlan() override {
+        if (d_desc) cudaFree(d_desc);
+        if (d_group_off) cudaFree(d_group_off);
+        if (d_tensor_off) cudaFree(d_tensor_off);
+        if (d_nodes) cudaFree(d_nodes);
+        if (d_tensors) cudaFree(d_tensors);
+    }
+};
+
+__global__ void __launch_bounds__(256)
+spline_lookup_kernel(int D, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
+                     const double *__restrict__ knots, const double *__restrict__ pts, int64_t N,
+                     int32_t *__restrict__ piece) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N;
+         q += (int64_t)gridDim.x * blockDim.x)
+        piece[q] = spline_piece_index(D, num_knots, knot_off, knots, pts + q * D);
+}
+
+__global__ void __launch_bounds__(PW_THREADS)
+spline_eval_kernel(int D, int G, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
+                   const double *__restrict__ knots, const GridDesc *__restrict__ desc,
+                   const double *__restrict__ nodes, const double *__restrict__ weights,
+                   const double *__restrict__ tensors, const double *__restrict__ pts, int64_t N,
+                   double *__restrict__ out, int32_t *__restrict__ piece_out) {
+    extern __shared__ __align__(16) double smem[];
+    double *ws = smem + threadIdx.x;
+    const int stride = blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const double *x = pts + q * D;
+        const int p = spline_piece_index(D, num_knots, knot_off, knots, x);
+        if (piece_out) piece_out[q] = p;
+        const GridDesc gd = desc[p];
+        int off = 0;
+        for (int d = 0; d < D; ++d) {
+            grid_weight_row(__ldg(x + d), gd.n[d], nodes + gd.node_off + off,
+                            weights + gd.node_off + off, ws + (size_t)off * stride, stride);
+            off += gd.n[d];
+        }
+        for (int g = 0; g < G; ++g)
+            out[q * G + g] = grid_contract(gd, tensors + gd.tensor_off + g * gd.size, ws, stride);
+    }
+}
+
+__global__ void __launch_bounds__(PW_THREADS)
+slider_eval_kernel(int D, int S, int G, double pivot, const GridDesc *__restrict__ desc,
+                   const int *__restrict__ group_off, const int *__restrict__ group_dims,
+                   const int *__restrict__ out_slide, const long long *__restrict__ tensor_off,
+                   const double *__restrict__ nodes, const double *__restrict__ weights,
+                   const double *__restrict__ tensors, const double *__restrict__ pts, int64_t N,
+                   double *__restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    double *ws = smem + threadIdx.x;
+    const int stride = blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const double *x = pts + q * D;
+        for (int g = 0; g < G; ++g) {
+            const int os = out_slide[g];
+            double result;
+            if (os == -2) {
+                result = 0.0;  // cross-slide mixed partial, slider.py:297-298
+            } else {
+                // value row: pivot + sum_s (slide_s - pivot), left to right (slider.py:310-318);
+                // derivative row: the owning slide only (slider.py:301-307)
+                result = os == -1 ? pivot : 0.0;
+                const int s_lo = os == -1 ? 0 : os, s_hi = os == -1 ? S : os + 1;
+                for (int s = s_lo; s < s_hi; ++s) {
+                    const GridDesc gd = desc[s];
+                    const int *dims = group_dims + group_off[s];
+                    int off = 0;
+                    for (int d = 0; d < gd.D; ++d) {
+                        grid_weight_row(__ldg(x + dims[d]), gd.n[d], nodes + gd.node_off + off,
+                                        weights + gd.node_off + off, ws + (size_t)off * stride, stride);
+                        off += gd.n[d];
+                    }
+                    const double v = grid_contract(gd, tensors + tensor_off[(size_t)g * S + s], ws, stride);
+                    result = os == -1 ? result + (v - pivot) : v;
+                }
+            }
+            out[q * G + g] = result;
+        }
+    }
+}
+
+template <typename T>
+static bool upload(T **dptr, const T *src, size_t count) {
+    if (count == 0) count = 1;
+    if (cudaMalloc(dptr, count * sizeof(T)) != cudaSuccess) return false;
+    return !src || cudaMemcpy(*dptr, src, count * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+static int grid_launch_dims(const PlanBase *pl, const void *kernel, int threads, size_t smem,
+                            int64_t N, int *grid) {
+    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    const int64_t want = (N + threads - 1) / threads;
+    const int64_t cap = (int64_t)pl->sm_count * (per_sm > 0 ? per_sm : 1);
+    *grid = (int)(want < cap ? want : cap);
+    return PCB_OK;
+}
+
+}  // namespace pcb
+
+using namespace pcb;
+
+extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num_knots, const double *knots_cat,
+                                      int P, const int32_t *piece_n, const double *piece_nodes_cat,
+                                      const double *piece_weights_cat, int G,
+                                      const double *const *piece_tensors_host, void **plan) {
+    PCB_REQUIRE(plan && num_knots && piece_n && piece_nodes_cat && piece_weights_cat &&
+                    piece_tensors_host, "null argument");
+    PCB_REQUIRE(D >= 1 && D <= GRID_MAXD, "num_dimensions %d outside [1, %d]", D, GRID_MAXD);
+    PCB_REQUIRE(G >= 1 && G <= 64, "number of derivative tensors %d outside [1, 64]", G);
+    long long expect = 1;
+    int total_knots = 0;
+    std::vector<int> meta(2 * D);
+    for (int d = 0; d < D; ++d) {
+        PCB_REQUIRE(num_knots[d] >= 0, "negative knot count");
+        meta[d] = num_knots[d];
+        meta[D + d] = total_knots;
+        total_knots += num_knots[d];
+        expect *= num_knots[d] + 1;
+    }
+    PCB_REQUIRE(expect == P, "num_pieces=%d does not match prod(num_knots+1)=%lld", P, expect);
+    PCB_REQUIRE(total_knots == 0 || knots_cat, "null knots");
+
+    SplinePlan *pl = new SplinePlan();
+    pl->kind = PLAN_SPLINE;
+    pl->dev = dev;
+    pl->D = D;
+    pl->P = P;
+    pl->G = G;
+    int cc = 0;
+    if (int rc = device_props(dev, &pl->sm_count, &pl->smem_optin, &cc)) {
+        delete pl;
+        return rc;
+    }
+    std::vector<GridDesc> desc(P);
+    long long node_total = 0, tensor_total = 0;
+    for (int p = 0; p < P; ++p) {
+        GridDesc &gd = desc[p];
+        memset(&gd, 0, sizeof(gd));
+        gd.D = D;
+        gd.size = 1;
+        gd.node_off = (int)node_total;
+        gd.tensor_off = tensor_total;
+        for (int d = 0; d < D; ++d) {
+            const int nn = piece_n[(size_t)p * D + d];
+            if (nn < 1) {
+                delete pl;
+                return fail(PCB_EINVAL, "piece %d: n_nodes[%d] must be >= 1", p, d);
+            }
+            gd.n[d] = nn;
+            gd.sum_n += nn;
+            gd.size *= nn;
+        }
+        node_total += gd.sum_n;
+        tensor_total += gd.size * G;
+        if (gd.sum_n > pl->max_sum_n) pl->max_sum_n = gd.sum_n;
+    }
+    DeviceGuard guard(dev);
+    bool ok = guard.ok && upload(&pl->d_num_knots, meta.data(), meta.size()) &&
+              upload(&pl->d_knots, knots_cat, (size_t)total_knots) &&
+              upload(&pl->d_desc, desc.data(), desc.size()) &&
+              upload<double>(&pl->d_nodes, nullptr, (size_t)(2 * node_total)) &&
+              upload<double>(&pl->d_tensors, nullptr, (size_t)tensor_total);
+    if (ok) {
+        pl->d_knot_off = pl->d_num_knots + D;
+        pl->d_weights = pl->d_nodes + node_total;
+        ok = cudaMemcpy(pl->d_nodes, piece_nodes_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(pl->d_weights, piece_weights_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+        for (int p = 0; ok && p < P; ++p)
+            for (int g = 0; ok && g < G; ++g)
+                ok = cudaMemcpy(pl->d_tensors + desc[p].tensor_off + g * desc[p].size,
+                                piece_tensors_host[(size_t)p * G + g], desc[p].size * 8,
+                                cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        delete pl;
+        return fail(PCB_ECUDA, "device allocation/upload for the spline plan failed");
+    }
+    *plan = pl;
+    return PCB_OK;
+}
+
+extern "C" PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int64_t N, int32_t *d_piece,
+                                 void *stream) {
+    SplinePlan *pl = static_cast<SplinePlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_SPLINE, "not a spline plan");
+    PCB_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return PCB_OK;
+    PCB_REQUIRE(d_points && d_piece, "null device pointer");
+    DeviceGuard guard(pl->dev);
+    const int64_t want = (N + 255) / 256;
+    const int64_t cap = (int64_t)pl->sm_count * 8;
+    spline_lookup_kernel<<<(int)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pl->D, pl->d_num_knots, pl->d_knot_off, pl->d_knots, d_points, N, d_piece);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}
+
+extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64_t N, double *d_out,
+                               int32_t *d_piece, void *stream) {
+    SplinePlan *pl = static_cast<SplinePlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_SPLINE, "not a spline plan");
+    PCB_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return PCB_OK;
+    PCB_REQUIRE(d_points && d_out, "null device pointer");
+    DeviceGuard guard(pl->dev);
+    const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
+    if (smem > (size_t)pl->smem_optin)
+        return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    int grid = 0;
+    if (int rc = grid_launch_dims(pl, (const void *)spline_eval_kernel, PW_THREADS, smem, N, &grid)) return rc;
+    spline_eval_kernel<<<grid, PW_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        pl->D, pl->G, pl->d_num_knots, pl->d_knot_off, pl->d_knots, pl->d_desc, pl->d_nodes,
+        pl->d_weights, pl->d_tensors, d_points, N, d_out, d_piece);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}
+
+extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32_t *group_size,
+                                      const int32_t *group_dims_cat, const int32_t *slide_n_cat,
+                                      const double *slide_nodes_cat, const double *slide_weights_cat,
+                                      double pivot_value, int G, const int32_t *out_slide,
+                                      const double *const *slide_tensors_host, void **plan) {
+    PCB_REQUIRE(plan && group_size && group_dims_cat && slide_n_cat && slide_nodes_cat &&
+                    slide_weights_cat && out_slide && slide_tensors_host, "null argument");
+    PCB_REQUIRE(D >= 1 && D <= 4096 && S >= 1 && S <= D, "invalid slider shape D=%d S=%d", D, S);
+    PCB_REQUIRE(G >= 1 && G <= 64, "number of output rows %d outside [1, 64]", G);
+    SliderPlan *pl = new SliderPlan();
+    pl->kind = PLAN_SLIDER;
+    pl->dev = dev;
+    pl->D = D;
+    pl->S = S;
+    pl->G = G;
+    pl->pivot = pivot_value;
+    int cc = 0;
+    if (int rc = device_props(dev, &pl->sm_count, &pl->smem_optin, &cc)) {
+        delete pl;
+        return rc;
+    }
+    std::vector<GridDesc> desc(S);
+    std::vector<int> ints;  // group_off [S+1] | group dims | out_slide [G]
+    ints.resize(S + 1);
+    int gpos = 0;
+    long long node_total = 0;
+    for (int s = 0; s < S; ++s) {
+        GridDesc &gd = desc[s];
+        memset(&gd, 0, sizeof(gd));
+        const int gs = group_size[s];
+        if (gs < 1 || gs > GRID_MAXD) {
+            delete pl;
+            return fail(PCB_EUNSUPPORTED, "slide %d has %d dims (supported: 1..%d)", s, gs, GRID_MAXD);
+        }
+        gd.D = gs;
+        gd.size = 1;
+        gd.node_off = (int)node_total;
+        ints[s] = gpos;
+        for (int d = 0; d < gs; ++d) {
+            const int dim = group_dims_cat[gpos + d];
+            const int nn = slide_n_cat[gpos + d];
+            if (dim < 0 || dim >= D || nn < 1) {
+                delete pl;
+                return fail(PCB_EINVAL, "slide %d: invalid dim/n_nodes", s);
+            }
+            gd.n[d] = nn;
+            gd.sum_n += nn;
+            gd.size *= nn;
+        }
+        gpos += gs;
+        node_total += gd.sum_n;
+        if (gd.sum_n > pl->max_sum_n) pl->max_sum_n = gd.sum_n;
+    }
+    ints[S] = gpos;
+    for (int i = 0; i < gpos; ++i) ints.push_back(group_dims_cat[i]);
+    for (int g = 0; g < G; ++g) {
+        if (out_slide[g] < -2 || out_slide[g] >= S) {
+            delete pl;
+            return fail(PCB_EINVAL, "out_slide[%d]=%d invalid", g, out_slide[g]);
+        }
+        ints.push_back(out_slide[g]);
+    }
+    // tensors actually referenced
+    std::vector<long long> toff((size_t)G * S, -1);
+    long long tensor_total = 0;
+    for (int g = 0; g < G; ++g)
+        for (int s = 0; s < S; ++s)
+            if (out_slide[g] == -1 || out_slide[g] == s) {
+                if (!slide_tensors_host[(size_t)g * S + s]) {
+                    delete pl;
+                    return fail(PCB_EINVAL, "missing tensor for row %d slide %d", g, s);
+                }
+                toff[(size_t)g * S + s] = tensor_total;
+                tensor_total += desc[s].size;
+            }
+    DeviceGuard guard(dev);
+    bool ok = guard.ok && upload(&pl->d_desc, desc.data(), desc.size()) &&
+              upload(&pl->d_group_off, ints.data(), ints.size()) &&
+              upload(&pl->d_tensor_off, toff.data(), toff.size()) &&
+              upload<double>(&pl->d_nodes, nullptr, (size_t)(2 * node_total)) &&
+              upload<double>(&pl->d_tensors, nullptr, (size_t)tensor_total);
+    if (ok) {
+        pl->d_group_dims = pl->d_group_off + S + 1;
+        pl->d_out_slide = pl->d_group_dims + gpos;
+        pl->d_weights = pl->d_nodes + node_total;
+        ok = cudaMemcpy(pl->d_nodes, slide_nodes_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(pl->d_weights, slide_weights_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+        for (int g = 0; ok && g < G; ++g)
+            for (int s = 0; ok && s < S; ++s)
+                if (toff[(size_t)g * S + s] >= 0)
+                    ok = cudaMemcpy(pl->d_tensors + toff[(size_t)g * S + s],
+                                    slide_tensors_host[(size_t)g * S + s], desc[s].size * 8,
+                                    cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        delete pl;
+        return fail(PCB_ECUDA, "device allocation/upload for the slider plan failed");
+    }
+    *plan = pl;
+    return PCB_OK;
+}
+
+extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream) {
+    SliderPlan *pl = static_cast<SliderPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_SLIDER, "not a slider plan");
+    PCB_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return PCB_OK;
+    PCB_REQUIRE(d_points && d_out, "null device pointer");
+    DeviceGuard guard(pl->dev);
+    const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
+    if (smem > (size_t)pl->smem_optin)
+        return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    int grid = 0;
+    if (int rc = grid_launch_dims(pl, (const void *)slider_eval_kernel, PW_THREADS, smem, N, &grid)) return rc;
+    slider_eval_kernel<<<grid, PW_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        pl->D, pl->S, pl->G, pl->pivot, pl->d_desc, pl->d_group_off, pl->d_group_dims, pl->d_out_slide,
+        pl->d_tensor_off, pl->d_nodes, pl->d_weights, pl->d_tensors, d_points, N, d_out);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}

@@ -1,0 +1,291 @@
+"""``ChebyshevTT``: Chebyshev interpolant in tensor-train format, evaluated on B200.
+
+Mirrors the reference class's constructor and evaluation entry points
+(``tensor_train.py:1088-1138, 2127-2463, 2870-2965``): ``eval`` / ``eval_batch`` /
+``eval_multi`` keep their signatures, finite-difference Greeks keep the reference's stencil
+(h = 1e-4 (b-a), boundary nudge, central differences).  The bodies call the CUDA engine
+(``pcb_tt_eval`` / ``pcb_tt_eval_fd``); there is no CPU evaluation path.
+
+Construction (``build``) is host NumPy: TT-SVD for moderate grids, or a rank-adaptive
+cross approximation for high-dimensional ones.  Cores made elsewhere (e.g. by the reference
+library) can be injected with :meth:`from_cores`.
+"""
+
+from __future__ import annotations
+
+import os
+import pickle
+import time
+from typing import List
+
+import numpy as np
+from scipy.fft import dct
+
+from . import _grid
+from ._engine import TTPlan, require_device
+from .approximation import _unwrap
+
+
+def values_to_coeffs(value_core: np.ndarray) -> np.ndarray:
+    """Values at the ascending first-kind Chebyshev nodes (axis 1) -> Chebyshev coefficients.
+
+    With the nodes listed from +1 down to -1 the expansion coefficients are the DCT-II of the
+    samples scaled by 1/n, with the constant term halved (reference ``tensor_train.py:997-1016``).
+    """
+    n = value_core.shape[1]
+    coeff = dct(value_core[:, ::-1, :], type=2, axis=1) / n
+    coeff[:, 0, :] *= 0.5
+    return coeff
+
+
+def tt_svd(tensor: np.ndarray, max_rank: int, tol: float) -> List[np.ndarray]:
+    """Sequential truncated-SVD tensor-train decomposition of a dense tensor (value cores).
+
+    At each unfolding singular values below ``tol * sigma_max`` are dropped and the rank is capped
+    at ``max_rank`` (same truncation rule as reference ``tensor_train.py:638-690``).
+    """
+    shape = list(tensor.shape)
+    cores = []
+    rest = np.asarray(tensor, dtype=np.float64)
+    r = 1
+    for k in range(len(shape) - 1):
+        mat = rest.reshape(r * shape[k], -1)
+        u, s, vt = np.linalg.svd(mat, full_matrices=False)
+        keep = min(max_rank, len(s))
+        if s[0] > 0:
+            keep = max(1, min(keep, int(np.sum(s > tol * s[0]))))
+        cores.append(u[:, :keep].reshape(r, shape[k], keep))
+        rest = np.diag(s[:keep]) @ vt[:keep, :]
+        r = keep
+    cores.append(rest.reshape(r, shape[-1], 1))
+    return cores
+
+
+class ChebyshevTT:
+    """Chebyshev interpolation in tensor-train format."""
+
+    def __init__(self, function, num_dimensions, domain, n_nodes, max_rank=10, tolerance=1e-6,
+                 max_sweeps=10, additional_data=None, *, max_derivative_order=2, device=None):
+        domain = _unwrap(domain, "bounds")
+        n_nodes = _unwrap(n_nodes, "counts")
+        if len(domain) != num_dimensions:
+            raise ValueError(
+                f"domain has {len(domain)} entries but num_dimensions={num_dimensions}")
+        if len(n_nodes) != num_dimensions:
+            raise ValueError(
+                f"n_nodes has {len(n_nodes)} entries but num_dimensions={num_dimensions}")
+        self.function = function
+        self.num_dimensions = num_dimensions
+        self.domain = domain
+        self.n_nodes = n_nodes
+        self.max_rank = max_rank
+        self.tolerance = tolerance
+        self.max_sweeps = max_sweeps
+        self.max_derivative_order = max_derivative_order
+        self.additional_data = additional_data
+        self.descriptor = ""
+        self.method = None
+        self.device = device
+        self._coeff_cores = None
+        self._tt_ranks = None
+        self._built = False
+        self._build_time = 0.0
+        self._total_build_evals = 0
+        # _dim_order[k] = user dimension stored at TT position k
+        self._dim_order = list(range(num_dimensions))
+        self._plans = {}
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def tt_ranks(self):
+        self._check_built()
+        return list(self._tt_ranks)
+
+    @property
+    def dim_order(self):
+        return list(self._dim_order)
+
+    @property
+    def compression_ratio(self) -> float:
+        self._check_built()
+        return float(np.prod(self.n_nodes)) / sum(c.size for c in self._coeff_cores)
+
+    @property
+    def build_time(self):
+        return self._build_time
+
+    @property
+    def total_build_evals(self):
+        return self._total_build_evals
+
+    def _check_built(self):
+        if not self._built:
+            raise RuntimeError("Call build() before using this method.")
+
+    # ------------------------------------------------------------------ construction
+    def build(self, verbose: bool | int = True, seed=None, method: str = "cross") -> None:
+        """Build the coefficient cores from ``function``.
+
+        ``method='svd'`` samples the whole grid and runs TT-SVD; ``method='cross'`` samples
+        O(d n r^2) fibres chosen by maximum-volume pivoting (see :mod:`._ttcross`).
+        """
+        if method not in ("cross", "svd", "als"):
+            raise ValueError(f"method must be 'cross', 'svd', or 'als', got {method!r}")
+        if method == "als":
+            raise NotImplementedError("method='als' is a build-time feature outside this package")
+        if self.function is None:
+            raise RuntimeError("Cannot build: no function assigned.")
+        t0 = time.time()
+        grids = [_grid.cheb_nodes(float(lo), float(hi), int(n))
+                 for (lo, hi), n in zip(self.domain, self.n_nodes)]
+        f, data = self.function, self.additional_data
+        if method == "svd":
+            pts = _grid.full_grid_points(grids)
+            vals = np.array([float(f(p, data)) for p in pts.tolist()]).reshape(self.n_nodes)
+            value_cores = tt_svd(vals, self.max_rank, self.tolerance)
+            n_evals = vals.size
+        else:
+            from ._ttcross import tt_cross
+
+            value_cores, n_evals = tt_cross(lambda p: float(f(p, data)), grids, self.max_rank,
+                                            self.tolerance, self.max_sweeps, seed)
+        self._install([values_to_coeffs(c) for c in value_cores])
+        self.method = method
+        self._total_build_evals = n_evals
+        self._build_time = time.time() - t0
+        if verbose:
+            print(f"  Built in {self._build_time:.3f}s ({n_evals:,} function evaluations); "
+                  f"TT ranks: {self._tt_ranks}")
+
+    def _install(self, coeff_cores):
+        self._coeff_cores = [np.ascontiguousarray(c, dtype=np.float64) for c in coeff_cores]
+        self._tt_ranks = [c.shape[0] for c in self._coeff_cores] + [self._coeff_cores[-1].shape[2]]
+        self._built = True
+        self._plans = {}
+
+    @classmethod
+    def from_values(cls, tensor_values, num_dimensions, domain, n_nodes, max_rank=None,
+                    tolerance=1e-6, max_derivative_order=2, additional_data=None, descriptor="",
+                    *, device=None) -> "ChebyshevTT":
+        """TT interpolant from a dense value tensor via TT-SVD (reference
+        ``tensor_train.py:2870-2965``)."""
+        domain = _unwrap(domain, "bounds")
+        n_nodes = _unwrap(n_nodes, "counts")
+        arr = np.asarray(tensor_values, dtype=np.float64)
+        if arr.shape != tuple(n_nodes):
+            raise ValueError(
+                f"tensor_values shape {arr.shape} does not match expected {tuple(n_nodes)}")
+        if not np.isfinite(arr).all():
+            raise ValueError("tensor_values contains NaN or Inf — all values must be finite")
+        if max_rank is None:
+            max_rank = max(n_nodes)
+        obj = cls(None, num_dimensions, list(domain), list(n_nodes), max_rank, tolerance,
+                  additional_data=additional_data, max_derivative_order=max_derivative_order,
+                  device=device)
+        obj.descriptor = descriptor
+        obj.method = "svd"
+        obj._install([values_to_coeffs(c) for c in tt_svd(arr, max_rank, tolerance)])
+        return obj
+
+    @classmethod
+    def from_cores(cls, coeff_cores, domain, dim_order=None, *, max_derivative_order=2,
+                   device=None) -> "ChebyshevTT":
+        """Wrap existing *coefficient* cores ``(r_{k-1}, n_k, r_k)`` (storage frame)."""
+        cores = [np.asarray(c, dtype=np.float64) for c in coeff_cores]
+        D = len(cores)
+        if len(domain) != D:
+            raise ValueError(f"domain has {len(domain)} entries but there are {D} cores")
+        if cores[0].shape[0] != 1 or cores[-1].shape[2] != 1:
+            raise ValueError("boundary TT ranks must be 1")
+        for k in range(D - 1):
+            if cores[k].shape[2] != cores[k + 1].shape[0]:
+                raise ValueError(f"rank mismatch between cores {k} and {k + 1}")
+        obj = cls(None, D, [list(b) for b in domain], [c.shape[1] for c in cores],
+                  max_rank=max(c.shape[2] for c in cores),
+                  max_derivative_order=max_derivative_order, device=device)
+        if dim_order is not None:
+            if sorted(int(v) for v in dim_order) != list(range(D)):
+                raise ValueError(f"dim_order must be a permutation of range({D})")
+            obj._dim_order = [int(v) for v in dim_order]
+        obj._install(cores)
+        return obj
+
+    @classmethod
+    def from_reference(cls, ref_tt, *, device=None) -> "ChebyshevTT":
+        """Adopt a built reference ``pychebyshev.ChebyshevTT`` (same cores, domain, dim order)."""
+        return cls.from_cores(ref_tt._coeff_cores, ref_tt.domain, ref_tt._dim_order,
+                              max_derivative_order=ref_tt.max_derivative_order, device=device)
+
+    # ------------------------------------------------------------------ device plan
+    def _plan(self, device=None) -> TTPlan:
+        self._check_built()
+        dev = require_device(self.device if device is None else device)
+        token = tuple(id(c) for c in self._coeff_cores)
+        hit = self._plans.get(dev)
+        if hit is None or hit[0] != token:
+            hit = (token, TTPlan(self._coeff_cores, self.domain, self.n_nodes, self._tt_ranks,
+                                 self._dim_order, dev))
+            self._plans[dev] = hit
+        return hit[1]
+
+    # ------------------------------------------------------------------ evaluation
+    def eval_batch(self, points, *, out=None, device=None):
+        """Values at N points (reference ``tensor_train.py:2217-2265``) -> (N,)."""
+        res = self._plan(device).eval(points, out)
+        return res.reshape(res.shape[0])
+
+    def eval(self, point) -> float:
+        """Single point (reference ``tensor_train.py:2127-2170``)."""
+        pts = np.asarray([list(point)], dtype=np.float64)
+        return float(self._plan().eval(pts)[0, 0])
+
+    def eval_multi_batch(self, points, derivative_orders, *, out=None, device=None, algo=0):
+        """Extension: value + finite-difference Greeks for N points in one launch -> (N, G).
+
+        Oracle: the reference's ``eval_multi`` called per point.
+        """
+        self._check_built()
+        orders = np.asarray([list(o) for o in derivative_orders], dtype=np.int64)
+        if orders.ndim != 2 or orders.shape[1] != self.num_dimensions:
+            raise ValueError(
+                f"each derivative order must have {self.num_dimensions} entries")
+        if (orders > 2).any():
+            bad = int(orders[orders > 2][0])
+            raise ValueError(f"Derivative order {bad} not supported (use 1 or 2)")
+        return self._plan(device).with_orders(orders, algo).eval(points, out)
+
+    def eval_multi(self, point, derivative_orders) -> List[float]:
+        """Value and central finite-difference derivatives at one point (reference
+        ``tensor_train.py:2267-2320``)."""
+        pts = np.asarray([list(point)], dtype=np.float64)
+        return [float(v) for v in self.eval_multi_batch(pts, derivative_orders)[0]]
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path) -> None:
+        """Pickle (the reference has no ``.pcb`` layout for tensor trains)."""
+        self._check_built()
+        with open(os.fspath(path), "wb") as f:
+            pickle.dump(self, f)
+
+    @classmethod
+    def load(cls, path) -> "ChebyshevTT":
+        with open(os.fspath(path), "rb") as f:
+            obj = pickle.load(f)
+        if not isinstance(obj, cls):
+            raise TypeError(f"Expected a {cls.__name__} instance, got {type(obj).__name__}")
+        return obj
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["function"] = None
+        state.pop("_plans", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._plans = {}
+
+    def __repr__(self):
+        ranks = self._tt_ranks if self._built else None
+        return (f"ChebyshevTT(dims={self.num_dimensions}, nodes={self.n_nodes}, ranks={ranks}, "
+                f"built={self._built}, backend='b200')")

@@ -1,0 +1,351 @@
+"""GPU parity: the CUDA path (through the Python classes -> ctypes -> C ABI) against the golden
+fixtures written by the reference and against the oracle on fresh seeded inputs.
+
+Tolerances (BASELINE.json north_star): piece indices bit-exact; values and full-tensor /
+spline / slider derivatives ``|d| <= 1e-12 |ref| + 1e-14``.  Two documented refinements:
+
+* values whose magnitude is far below the interpolant's scale (deep out-of-the-money prices that
+  are the sum of O(10) terms cancelling to 1e-5) cannot agree to 1e-12 *relative* between any two
+  summation orders -- the reference's own ``eval`` and ``eval_batch`` differ by 1.6e-13 there
+  (SURVEY.md App. B.2).  The absolute floor is therefore taken relative to the interpolant's
+  scale: ``1e-14 * max|ref|``.
+* TT Greeks are finite differences: the value tolerance is propagated through the stencil,
+  ``|d| <= c (1e-12 max|f| + 1e-14) / h^p``.
+"""
+
+import numpy as np
+import pytest
+
+import _golden as G
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def scale_close(got, ref, what, rel=1e-12, floor=1e-14):
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = max(1.0, float(np.max(np.abs(ref)))) if ref.size else 1.0
+    G.assert_close(got, ref, rel=rel, abs_=floor * scale, what=what)
+
+
+# ------------------------------------------------------------------------------------------
+# tensor train
+# ------------------------------------------------------------------------------------------
+
+TT_CASES = ["tt_bs5d", "tt_4d", "tt_4d_perm", "tt_basket10d", "tt_rank20_10d"]
+
+
+def _tt(name):
+    import pychebyshev_b200 as pcb
+
+    g = G.load(name)
+    cores, domain, dim_order = G.tt_parts(g)
+    return g, pcb.ChebyshevTT.from_cores(cores, domain, dim_order)
+
+
+@pytest.mark.parametrize("name", TT_CASES)
+def test_tt_eval_batch_matches_reference(name):
+    g, tt = _tt(name)
+    got = tt.eval_batch(g["points"])
+    assert got.shape == g["values"].shape
+    scale_close(got, g["values"], f"{name} eval_batch")
+
+
+@pytest.mark.parametrize("name", TT_CASES)
+def test_tt_device_resident_matches_host_path(name):
+    import torch
+
+    g, tt = _tt(name)
+    d_pts = torch.from_numpy(g["points"]).cuda()
+    got = tt.eval_batch(d_pts)
+    assert got.is_cuda and got.dtype == torch.float64
+    assert np.array_equal(got.cpu().numpy(), tt.eval_batch(g["points"]))
+
+
+def fd_tolerance(g, domain, dim_order):
+    """Propagated tolerance per (point, row): c * (1e-12 * scale + 1e-14) / h^p."""
+    orders = g["fd_orders"]
+    D = orders.shape[1]
+    scale = float(np.max(np.abs(g["fd_single_values"])))
+    base = 1e-12 * scale + 1e-14
+    tol = np.empty(orders.shape[0])
+    for r, o in enumerate(orders):
+        t = base
+        for user_dim, k in enumerate(o):
+            if k == 0:
+                continue
+            s = dim_order.index(user_dim)
+            h = (domain[s][1] - domain[s][0]) * 1e-4
+            t = t * (1.0 / h if k == 1 else 4.0 / (h * h))
+        tol[r] = t
+    del D
+    return tol
+
+
+@pytest.mark.parametrize("name", TT_CASES)
+def test_tt_fd_greeks_match_reference(name):
+    g, tt = _tt(name)
+    cores, domain, dim_order = G.tt_parts(g)
+    got = tt.eval_multi_batch(g["fd_points"], g["fd_orders"], algo=1)
+    ref = g["fd_values"]
+    assert got.shape == ref.shape
+    tol = fd_tolerance(g, domain, dim_order)
+    err = np.abs(got - ref)
+    bad = err > tol[None, :]
+    assert not bad.any(), (
+        f"{name}: {int(bad.sum())} FD entries outside the propagated tolerance; worst ratio "
+        f"{float(np.max(err / tol[None, :])):.3g}")
+    # value rows (all-zero orders) are plain values: the flat tolerance applies
+    for r, o in enumerate(g["fd_orders"]):
+        if not o.any():
+            scale_close(got[:, r], ref[:, r], f"{name} eval_multi value row")
+
+
+def test_tt_order3_raises_like_reference():
+    g, tt = _tt("tt_4d")
+    with pytest.raises(ValueError, match="not supported"):
+        tt.eval_multi([0.1, 0.5, 1.0, -1.0], [[3, 0, 0, 0]])
+
+
+def test_tt_single_point_api():
+    g, tt = _tt("tt_bs5d")
+    p = g["fd_points"][3]
+    v = tt.eval(list(p))
+    scale_close(np.array([v]), g["fd_single_values"][3:4], "eval single", floor=1e-13)
+    multi = tt.eval_multi(list(p), [list(o) for o in g["fd_orders"][:4]])
+    assert len(multi) == 4 and abs(multi[0] - v) <= 1e-12 * abs(v) + 1e-13
+
+
+def test_tt_oracle_fresh_seed_large_batch():
+    """Fresh inputs (not in the fixture), ragged size, against the oracle."""
+    g, tt = _tt("tt_bs5d")
+    cores, domain, dim_order = G.tt_parts(g)
+    rng = np.random.default_rng(2024)
+    dom = np.array(domain)
+    n = 100_003  # not a multiple of the tile size
+    pts = rng.uniform(dom[:, 0], dom[:, 1], size=(n, 5))
+    scale_close(tt.eval_batch(pts), O.tt_eval_batch(cores, domain, dim_order, pts), "fresh batch")
+
+
+def test_tt_empty_and_single_row():
+    g, tt = _tt("tt_4d")
+    assert tt.eval_batch(np.zeros((0, 4))).shape == (0,)
+    one = tt.eval_batch(g["points"][:1])
+    scale_close(one, g["values"][:1], "N=1")
+
+
+# ------------------------------------------------------------------------------------------
+# full tensor
+# ------------------------------------------------------------------------------------------
+
+FULL_SMALL = ["full_1d", "full_2d", "full_3d", "full_4d"]
+
+
+def _full(name, tensor=None):
+    import pychebyshev_b200 as pcb
+
+    g = G.load(name)
+    if tensor is None:
+        tensor = g["tensor"]
+    n = [int(v) for v in g["n_nodes"]]
+    dom = [list(map(float, r)) for r in g["domain"]]
+    return g, pcb.ChebyshevApproximation.from_values(tensor, len(n), dom, n)
+
+
+@pytest.mark.parametrize("name", FULL_SMALL)
+@pytest.mark.parametrize("algo", [1, 2])
+def test_full_small_matches_reference(name, algo):
+    g, cheb = _full(name)
+    if algo == 2 and cheb.num_dimensions < 2:
+        pytest.skip("tensor-core path needs D >= 2")
+    got = cheb.eval_batch_multi(g["points"], g["orders"], algo=algo)
+    assert got.shape == g["values"].shape
+    for r in range(got.shape[1]):
+        scale_close(got[:, r], g["values"][:, r], f"{name} algo={algo} order={g['orders'][r]}")
+
+
+def test_full_per_order_api_matches_multi():
+    g, cheb = _full("full_3d")
+    multi = cheb.eval_batch_multi(g["points"], g["orders"])
+    for r, o in enumerate(g["orders"]):
+        single = cheb.vectorized_eval_batch(g["points"], [int(v) for v in o])
+        assert single.shape == (len(g["points"]),)
+        scale_close(single, g["values"][:, r], f"vectorized_eval_batch {o}")
+        assert np.array_equal(single, multi[:, r]) or np.allclose(single, multi[:, r], rtol=1e-13)
+    did = cheb.get_derivative_id([1, 0, 0])
+    by_id = cheb.vectorized_eval_batch(g["points"], derivative_id=did)
+    scale_close(by_id, g["values"][:, 1], "derivative_id")
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_full_bs5d_price_and_greeks(algo):
+    """BASELINE config 1: 11^5 Black-Scholes, price + delta/gamma/vega (+rho, +cross)."""
+    from pychebyshev_b200 import workloads as wl
+
+    g = G.load("full_bs5d")
+    nodes = G.split(g["nodes_cat"], [int(v) for v in g["n_nodes"]])
+    tensor = wl.grid_values(wl.bs_call_price, nodes)
+    g2, cheb = _full("full_bs5d", tensor)
+    for d in range(5):
+        assert np.array_equal(cheb.nodes[d], nodes[d])
+    got = cheb.eval_batch_multi(g["points"], g["orders"], algo=algo)
+    for r in range(got.shape[1]):
+        scale_close(got[:, r], g["values"][:, r], f"bs5d algo={algo} order={g['orders'][r]}")
+
+
+def test_full_c4_16p6_tensor_core_path():
+    """BASELINE config 4: 16^6 (134 MB per tensor), DMMA path, parity on the stored points."""
+    from pychebyshev_b200 import workloads as wl
+
+    g = G.load("full_c4_16p6")
+    nodes = G.split(g["nodes_cat"], [int(v) for v in g["n_nodes"]])
+    tensor = wl.grid_values(wl.bs6d, nodes)
+    g2, cheb = _full("full_c4_16p6", tensor)
+    got = cheb.eval_batch_multi(g["points"], g["orders"], algo=2)
+    for r in range(got.shape[1]):
+        scale_close(got[:, r], g["values"][:, r], f"c4 order={g['orders'][r]}")
+
+
+def test_full_single_point_and_errors():
+    g, cheb = _full("full_2d")
+    p = [float(v) for v in g["points"][0]]
+    v = cheb.vectorized_eval(p, [0, 0])
+    scale_close(np.array([v]), g["values"][0:1, 0], "vectorized_eval")
+    multi = cheb.vectorized_eval_multi(p, [[0, 0], [1, 0]])
+    scale_close(np.array(multi), g["values"][0, :2], "vectorized_eval_multi")
+    with pytest.raises(ValueError):
+        cheb.vectorized_eval_batch(g["points"])
+    with pytest.raises(ValueError):
+        cheb.vectorized_eval_batch(g["points"], [0, 0], derivative_id=0)
+    with pytest.raises(KeyError):
+        cheb.vectorized_eval_batch(g["points"], derivative_id=99)
+
+
+# ------------------------------------------------------------------------------------------
+# spline
+# ------------------------------------------------------------------------------------------
+
+SPLINES = ["spline_abs1d", "spline_bs2d", "spline_bs3d", "spline_multiknot3d", "spline_nested2d"]
+
+
+def _spline(name):
+    import pychebyshev_b200 as pcb
+    from pychebyshev_b200 import ChebyshevApproximation
+
+    g = G.load(name)
+    knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+    dom = [list(map(float, r)) for r in g["domain"]]
+    D = len(dom)
+    if bool(g["nested"]):
+        # nested n_nodes: assemble through the constructor + per-piece values
+        per_dim = [[] for _ in range(D)]
+        for idx, (t, nodes, w, dm) in zip(np.ndindex(*shape), pieces):
+            for d in range(D):
+                if len(per_dim[d]) <= idx[d]:
+                    per_dim[d].append(len(nodes[d]))
+        sp = pcb.ChebyshevSpline(None, D, dom, per_dim, knots, defer_build=True)
+        for piece, (t, nodes, w, dm) in zip(sp._pieces, pieces):
+            piece.set_original_function_values(t)
+        sp._built = True
+    else:
+        n = [int(v) for v in g["piece_n_nodes"][0]]
+        sp = pcb.ChebyshevSpline.from_values([p[0] for p in pieces], D, dom, n, knots)
+    for piece, (t, nodes, w, dm) in zip(sp._pieces, pieces):
+        assert isinstance(piece, ChebyshevApproximation)
+        for d in range(D):
+            assert np.array_equal(piece.nodes[d], nodes[d])
+            assert np.array_equal(piece.weights[d], w[d])
+    return g, sp
+
+
+@pytest.mark.parametrize("name", SPLINES)
+def test_spline_lookup_bit_exact(name):
+    g, sp = _spline(name)
+    got = sp.find_pieces(g["points"])
+    assert got.dtype == np.int32
+    assert np.array_equal(got, g["piece"])
+    if len(g["lookup_points"]):
+        assert np.array_equal(sp.find_pieces(g["lookup_points"]), g["lookup_piece"])
+
+
+@pytest.mark.parametrize("name", SPLINES)
+def test_spline_eval_batch_matches_reference(name):
+    g, sp = _spline(name)
+    got = sp.eval_batch_multi(g["points"], g["orders"])
+    for r, o in enumerate(g["orders"]):
+        scale_close(got[:, r], g["values"][:, r], f"{name} order={o}")
+        one = sp.eval_batch(g["points"], [int(v) for v in o])
+        assert np.array_equal(one, got[:, r]) or np.allclose(one, got[:, r], rtol=1e-13, atol=0)
+
+
+def test_spline_single_point_knot_rule():
+    g, sp = _spline("spline_bs2d")
+    # value at the knot is fine, derivative at the knot raises (spline.py:519-550)
+    assert abs(sp.eval([100.0, 0.5], [0, 0])) < 1e-10
+    with pytest.raises(ValueError, match="not defined at knot"):
+        sp.eval([100.0, 0.5], [1, 0])
+    with pytest.raises(ValueError, match="not defined at knot"):
+        sp.eval_multi([100.0, 0.5], [[0, 0], [1, 0]])
+    # batch: silently the right-hand piece
+    out = sp.eval_batch(np.array([[100.0, 0.5]]), [1, 0])
+    assert np.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------------
+# slider
+# ------------------------------------------------------------------------------------------
+
+def test_slider_matches_reference():
+    import pychebyshev_b200 as pcb
+
+    g = G.load("slider10d")
+    part, pivot_value, slides = G.slider_parts(g, O.diff_matrix)
+    dom = [list(map(float, r)) for r in g["domain"]]
+    n = [int(v) for v in g["n_nodes"]]
+    sl = pcb.ChebyshevSlider.from_slides([s[0] for s in slides], 10, dom, n, part,
+                                         list(g["pivot_point"]), pivot_value)
+    got = sl.eval_batch_multi(g["points"], g["orders"])
+    ref = g["values"]
+    for r, o in enumerate(g["orders"]):
+        active = {sl._dim_to_slide[d] for d, k in enumerate(o) if k > 0}
+        if len(active) > 1:
+            assert np.array_equal(got[:, r], np.zeros(len(ref)))  # exactly 0.0
+        else:
+            # derivative rows: the reference's single-point path interleaves the D^T passes with
+            # the contraction; its own paths differ by up to ~5e-12 there
+            rel = 1e-12 if not active else 2e-11
+            scale_close(got[:, r], ref[:, r], f"slider order={o}", rel=rel)
+    v = sl.eval([float(x) for x in g["points"][5]], [0] * 10)
+    scale_close(np.array([v]), ref[5:6, 0], "slider.eval")
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at scale (BASELINE sizes do not fit a CPU oracle)
+# ------------------------------------------------------------------------------------------
+
+def test_tt_large_batch_properties():
+    """1e7 queries on device: chunk invariance, permutation equivariance, idempotence."""
+    import torch
+
+    g, tt = _tt("tt_bs5d")
+    cores, domain, dim_order = G.tt_parts(g)
+    n = 10_000_000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    lo = torch.tensor([d[0] for d in domain], device="cuda", dtype=torch.float64)
+    hi = torch.tensor([d[1] for d in domain], device="cuda", dtype=torch.float64)
+    pts = lo + (hi - lo) * torch.rand((n, 5), generator=gen, device="cuda", dtype=torch.float64)
+    full = tt.eval_batch(pts)
+    again = tt.eval_batch(pts)
+    assert torch.equal(full, again)  # idempotent / deterministic
+    # a query's value does not depend on where it sits in the batch or on the batch size
+    perm = torch.randperm(n, generator=gen, device="cuda")
+    assert torch.equal(tt.eval_batch(pts[perm]), full[perm])
+    assert torch.equal(tt.eval_batch(pts[123_457:1_234_567]), full[123_457:1_234_567])
+    # spot-check a slice against the oracle
+    idx = torch.arange(0, n, n // 2000, device="cuda")
+    ref = O.tt_eval_batch(cores, domain, dim_order, pts[idx].cpu().numpy())
+    scale_close(full[idx].cpu().numpy(), ref, "1e7 spot check")
+    # FD rows: value row identical to eval_batch, rows finite
+    fd = tt.eval_multi_batch(pts[:1_000_000], g["fd_orders"][:4], algo=1)
+    assert torch.isfinite(fd).all()
+    scale_close(fd[:, 0].cpu().numpy(), full[:1_000_000].cpu().numpy(), "fd value row", rel=1e-13)
