@@ -90,3 +90,85 @@ def assert_close(got, ref, rel=REL, abs_=ABS, what=""):
             f"{what}: {int(bad.sum())}/{bad.size} outside {rel:g}*|ref|+{abs_:g}; worst at flat "
             f"index {i}: got {got.flat[i]!r} ref {ref.flat[i]!r} err {err.flat[i]:.3e}"
         )
+
+
+def extrapolation_factor(domain, nodes, weights, points):
+    """Per-point tolerance multiplier: 1 inside the domain, the Lebesgue function
+    prod_d sum_i |l_i(x_d)| outside it.
+
+    Barycentric *extrapolation* is ill-conditioned: any two summation orders (the reference's own
+    evaluation paths included) differ by ~eps * Lebesgue(x) * max|f| there, so the flat 1e-12
+    bound is only meaningful inside the domain, where the interpolant is meant to be used.
+    """
+    pts = np.asarray(points, dtype=np.float64)
+    fac = np.ones(pts.shape[0])
+    for d in range(pts.shape[1]):
+        lo, hi = domain[d]
+        out = (pts[:, d] < lo) | (pts[:, d] > hi)
+        if not out.any():
+            continue
+        diff = pts[out, d][:, None] - nodes[d][None, :]
+        w = weights[d][None, :] / diff
+        lam = np.sum(np.abs(w), axis=1) / np.abs(np.sum(w, axis=1))
+        fac[out] *= np.maximum(lam, 1.0)
+    return fac
+
+
+def assert_close_scaled(got, ref, factor, what, rel=REL, floor=ABS):
+    """|got - ref| <= factor * (rel * |ref| + floor * max(1, max|ref|))."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    finite = np.isfinite(ref)
+    scale = max(1.0, float(np.max(np.abs(ref[finite])))) if finite.any() else 1.0
+    tol = factor * (rel * np.abs(ref) + floor * scale)
+    err = np.abs(got - ref)
+    bad = ~(err <= tol) & finite
+    if bad.any():
+        i = int(np.argmax(np.where(bad, err / np.maximum(tol, 1e-300), 0.0)))
+        raise AssertionError(
+            f"{what}: {int(bad.sum())}/{bad.size} outside tolerance; worst at {i}: got "
+            f"{got.flat[i]!r} ref {ref.flat[i]!r} err {err.flat[i]:.3e} tol {tol.flat[i]:.3e}")
+
+
+def fd_tolerance(g, domain, dim_order):
+    """Propagated finite-difference tolerance per output row:
+    ``c * (1e-12 * max|f| + 1e-14) / h^p`` with (c, p) = (1, 1) per first-order dim and
+    (4, 2) per second-order dim (nested stencils multiply)."""
+    orders = g["fd_orders"]
+    scale = float(np.max(np.abs(g["fd_single_values"])))
+    base = 1e-12 * scale + 1e-14
+    tol = np.empty(orders.shape[0])
+    for r, o in enumerate(orders):
+        t = base
+        for user_dim, k in enumerate(o):
+            if k == 0:
+                continue
+            s = dim_order.index(user_dim)
+            h = (domain[s][1] - domain[s][0]) * 1e-4
+            t = t * (1.0 / h if k == 1 else 4.0 / (h * h))
+        tol[r] = t
+    return tol
+
+
+def spline_factor(g, knots, pieces):
+    """Extrapolation factor w.r.t. the piece each point is routed to."""
+    pts = g["points"]
+    fac = np.ones(len(pts))
+    for p in np.unique(g["piece"]):
+        t, nodes, w, dm = pieces[p]
+        # the piece's sub-domain: nodes are strictly inside it, so recover it from the fixture
+        dom = piece_domain(g, knots, p)
+        m = g["piece"] == p
+        fac[m] = extrapolation_factor(dom, nodes, w, pts[m])
+    return fac
+
+
+def piece_domain(g, knots, flat):
+    shape = [int(v) for v in g["shape"]]
+    idx = np.unravel_index(int(flat), shape)
+    dom = []
+    for d, (lo, hi) in enumerate(g["domain"]):
+        edges = [float(lo)] + list(knots[d]) + [float(hi)]
+        dom.append((edges[idx[d]], edges[idx[d] + 1]))
+    return dom

@@ -22,10 +22,8 @@ from oracle import np_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def scale_close(got, ref, what, rel=1e-12, floor=1e-14):
-    ref = np.asarray(ref, dtype=np.float64)
-    scale = max(1.0, float(np.max(np.abs(ref)))) if ref.size else 1.0
-    G.assert_close(got, ref, rel=rel, abs_=floor * scale, what=what)
+def scale_close(got, ref, what, rel=1e-12, floor=1e-14, factor=1.0):
+    G.assert_close_scaled(got, ref, factor, what, rel=rel, floor=floor)
 
 
 # ------------------------------------------------------------------------------------------
@@ -62,26 +60,6 @@ def test_tt_device_resident_matches_host_path(name):
     assert np.array_equal(got.cpu().numpy(), tt.eval_batch(g["points"]))
 
 
-def fd_tolerance(g, domain, dim_order):
-    """Propagated tolerance per (point, row): c * (1e-12 * scale + 1e-14) / h^p."""
-    orders = g["fd_orders"]
-    D = orders.shape[1]
-    scale = float(np.max(np.abs(g["fd_single_values"])))
-    base = 1e-12 * scale + 1e-14
-    tol = np.empty(orders.shape[0])
-    for r, o in enumerate(orders):
-        t = base
-        for user_dim, k in enumerate(o):
-            if k == 0:
-                continue
-            s = dim_order.index(user_dim)
-            h = (domain[s][1] - domain[s][0]) * 1e-4
-            t = t * (1.0 / h if k == 1 else 4.0 / (h * h))
-        tol[r] = t
-    del D
-    return tol
-
-
 @pytest.mark.parametrize("name", TT_CASES)
 def test_tt_fd_greeks_match_reference(name):
     g, tt = _tt(name)
@@ -89,7 +67,7 @@ def test_tt_fd_greeks_match_reference(name):
     got = tt.eval_multi_batch(g["fd_points"], g["fd_orders"], algo=1)
     ref = g["fd_values"]
     assert got.shape == ref.shape
-    tol = fd_tolerance(g, domain, dim_order)
+    tol = G.fd_tolerance(g, domain, dim_order)
     err = np.abs(got - ref)
     bad = err > tol[None, :]
     assert not bad.any(), (
@@ -152,6 +130,11 @@ def _full(name, tensor=None):
     return g, pcb.ChebyshevApproximation.from_values(tensor, len(n), dom, n)
 
 
+def _full_factor(g, cheb):
+    """1 inside the domain, the Lebesgue function outside (see _golden.extrapolation_factor)."""
+    return G.extrapolation_factor(cheb.domain, cheb.nodes, cheb.weights, g["points"])
+
+
 @pytest.mark.parametrize("name", FULL_SMALL)
 @pytest.mark.parametrize("algo", [1, 2])
 def test_full_small_matches_reference(name, algo):
@@ -160,8 +143,10 @@ def test_full_small_matches_reference(name, algo):
         pytest.skip("tensor-core path needs D >= 2")
     got = cheb.eval_batch_multi(g["points"], g["orders"], algo=algo)
     assert got.shape == g["values"].shape
+    fac = _full_factor(g, cheb)
     for r in range(got.shape[1]):
-        scale_close(got[:, r], g["values"][:, r], f"{name} algo={algo} order={g['orders'][r]}")
+        scale_close(got[:, r], g["values"][:, r], f"{name} algo={algo} order={g['orders'][r]}",
+                    factor=fac)
 
 
 def test_full_per_order_api_matches_multi():
@@ -189,8 +174,10 @@ def test_full_bs5d_price_and_greeks(algo):
     for d in range(5):
         assert np.array_equal(cheb.nodes[d], nodes[d])
     got = cheb.eval_batch_multi(g["points"], g["orders"], algo=algo)
+    fac = _full_factor(g, cheb)
     for r in range(got.shape[1]):
-        scale_close(got[:, r], g["values"][:, r], f"bs5d algo={algo} order={g['orders'][r]}")
+        scale_close(got[:, r], g["values"][:, r], f"bs5d algo={algo} order={g['orders'][r]}",
+                    factor=fac)
 
 
 def test_full_c4_16p6_tensor_core_path():
@@ -202,8 +189,9 @@ def test_full_c4_16p6_tensor_core_path():
     tensor = wl.grid_values(wl.bs6d, nodes)
     g2, cheb = _full("full_c4_16p6", tensor)
     got = cheb.eval_batch_multi(g["points"], g["orders"], algo=2)
+    fac = _full_factor(g, cheb)
     for r in range(got.shape[1]):
-        scale_close(got[:, r], g["values"][:, r], f"c4 order={g['orders'][r]}")
+        scale_close(got[:, r], g["values"][:, r], f"c4 order={g['orders'][r]}", factor=fac)
 
 
 def test_full_single_point_and_errors():
@@ -272,8 +260,10 @@ def test_spline_lookup_bit_exact(name):
 def test_spline_eval_batch_matches_reference(name):
     g, sp = _spline(name)
     got = sp.eval_batch_multi(g["points"], g["orders"])
+    knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+    fac = G.spline_factor(g, knots, pieces)
     for r, o in enumerate(g["orders"]):
-        scale_close(got[:, r], g["values"][:, r], f"{name} order={o}")
+        scale_close(got[:, r], g["values"][:, r], f"{name} order={o}", factor=fac)
         one = sp.eval_batch(g["points"], [int(v) for v in o])
         assert np.array_equal(one, got[:, r]) or np.allclose(one, got[:, r], rtol=1e-13, atol=0)
 
