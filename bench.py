@@ -258,6 +258,7 @@ def run_ours(args, rank, local_rank, world):
                                                dtype=torch.float64)
     out = torch.empty((n, G), dtype=torch.float64, device=dev)
     plan = tt._plan(local_rank).with_orders(np.asarray(orders), args.algo)
+    args.algo = plan.resolved_algo()
 
     def barrier():
         if world > 1:
@@ -402,8 +403,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.algo == 0:
-        args.algo = resolve_auto_algo()
     try:
         run_ours(args, rank, local_rank, world)
     finally:
@@ -411,15 +410,6 @@ def main():
             import torch.distributed as dist
 
             dist.destroy_process_group()
-
-
-def resolve_auto_algo():
-    """The algo ``pcb_tt_eval_fd(algo=0)`` picks for price/delta/gamma/vega (one active dim per
-    row): 2 (shared partial products) when the library provides it, else 1."""
-    from pychebyshev_b200 import _lib
-
-    lib = _lib.load()
-    return 2 if hasattr(lib, "pcb_tt_fd_shared_available") and lib.pcb_tt_fd_shared_available() else 1
 
 
 if __name__ == "__main__":

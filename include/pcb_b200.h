@@ -76,6 +76,9 @@ PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N, double *d
 PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G, const int32_t *orders,
                    double *d_out, int algo, void *stream);
 
+/* Which algorithm pcb_tt_eval_fd(algo = 0) runs for these rows: 1 or 2; negative PCB_E* on error. */
+PCB_API int pcb_tt_fd_algo(void *plan, int G, const int32_t *orders);
+
 /* ---------------------------------------------------------------------------------------------
  * ChebyshevApproximation   (barycentric.py)
  * ------------------------------------------------------------------------------------------ */

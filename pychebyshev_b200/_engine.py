@@ -253,6 +253,18 @@ class TTPlan(DevicePlan):
         view.algo = algo
         return view
 
+    def resolved_algo(self) -> int:
+        """The algorithm ``pcb_tt_eval_fd`` runs for this view's rows (1 or 2)."""
+        if self._orders is None:
+            return 0
+        if self.algo:
+            return self.algo
+        handle = self._handle if self._handle else self._owner._handle
+        rc = _lib.load().pcb_tt_fd_algo(handle, self.G, self._orders)
+        if rc < 0:
+            _lib.check(rc)
+        return rc
+
     def _launch(self, d_points, n, d_out, stream):
         lib = _lib.load()
         handle = self._handle if self._handle else self._owner._handle

@@ -31,6 +31,10 @@ struct TTParams {
     int rp[PCB_MAX_DIMS];    // r[k+1] rounded up to even: row stride of packed core k
     int off[PCB_MAX_DIMS];   // offset (doubles) of packed core k: [i][j][rp]
     int perm[PCB_MAX_DIMS];  // storage position k -> user column
+    int totalT;              // doubles in the packed transposed cores (stored after the forward ones)
+    int rpT[PCB_MAX_DIMS];   // r[k] rounded up to even: row stride of transposed core k
+    int offT[PCB_MAX_DIMS];  // offset (doubles, from the start of the buffer) of transposed core k:
+                             // [l][j][rpT] with GT[l][j][i] = G[i][j][l]
     double lo[PCB_MAX_DIMS];
     double hi[PCB_MAX_DIMS];
 };
@@ -47,10 +51,20 @@ struct TTFdProgram {
     TTFdRow row[TT_MAX_G];
 };
 
+// pcb_tt_eval_fd algo 2: every row differentiates at most one dim.
+struct TTSharedProgram {
+    int G;
+    int n_slots;                 // distinct differentiated storage dims, ascending
+    int slot_dim[TT_MAX_G];
+    int row_slot[TT_MAX_G];      // -1 value row, else index into slot_dim
+    int row_ord[TT_MAX_G];       // 1 or 2
+};
+
 struct TTPlan : PlanBase {
     TTParams P;
     double *d_cores = nullptr;
     int mode = TT_RESIDENT;
+    int mode_shared = TT_RESIDENT;
     int pingpong = 0;
     ~TTPlan() override {
         if (d_cores) cudaFree(d_cores);
@@ -378,6 +392,231 @@ tt_fd_general_kernel(const __grid_constant__ TTParams P, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
+// algo 2: shared left/right partial products
+//
+// With every stencil point differing from the query in ONE coordinate a, the interpolant along
+// that coordinate is the degree n_a-1 Chebyshev series  f(x_a) = sum_j y_j T_j(s(x_a)),
+//   y_j = L_a . G_a[:, j, :] . R_{a+1},
+// L_a = product of the contracted cores left of a, R_{a+1} = product right of a, both at the
+// query's own coordinates.  One left sweep (continued from slot to slot), one right sweep per
+// differentiated dim and one coefficient pass give every stencil value of that dim for n_a FMAs
+// each, instead of a full chain per stencil point.  The finite-difference formulas, step h and
+// boundary nudge are the reference's (tensor_train.py:2356-2403).
+// ---------------------------------------------------------------------------------------------
+
+struct TTSharedSmem {
+    int cores;
+    int v;      // [nbuf][rmaxp][QPT][threads]
+    int total;
+};
+
+__host__ __device__ inline TTSharedSmem tt_shared_smem_layout(const TTParams &P, int mode,
+                                                              int pingpong, int qpt, int threads) {
+    TTSharedSmem L;
+    L.cores = 0;
+    const int core_area =
+        mode == TT_RESIDENT ? P.total + P.totalT : (mode == TT_STREAM ? P.maxcore : 0);
+    L.v = (core_area + 1) & ~1;
+    L.total = L.v + (2 + (pingpong ? 1 : 0)) * P.rmaxp * qpt * threads;
+    L.total = (L.total + 1) & ~1;
+    return L;
+}
+
+// Fetch one packed core (forward or transposed) for the whole CTA.
+template <int MODE>
+__device__ __forceinline__ const double *tt_core_ptr(const double *__restrict__ g_cores, double *smem,
+                                                     int cores_off, int off, int count) {
+    if (MODE == TT_RESIDENT) return smem + cores_off + off;
+    if (MODE == TT_STREAM) {
+        __syncthreads();
+        const double2 *src = reinterpret_cast<const double2 *>(g_cores + off);
+        double2 *dst = reinterpret_cast<double2 *>(smem + cores_off);
+        for (int e = threadIdx.x; e < count / 2; e += blockDim.x) dst[e] = src[e];
+        __syncthreads();
+        return smem + cores_off;
+    }
+    return g_cores + off;
+}
+
+// One chunk of the coefficient pass: y += sum_l (sum_i L[i] g[i][j][l0+l]) * R[l0+l]
+template <int W, int QPT>
+__device__ __forceinline__ void tt_coeff_chunk(const double *__restrict__ gj, int istride, int r_in,
+                                               const double *vL, const double *vR, int vstride,
+                                               double (&y)[QPT]) {
+    double acc[QPT][W];
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+        for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < r_in; ++i) {
+        double li[QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) li[qq] = vL[(i * QPT + qq) * vstride];
+        const double *gi = gj + (size_t)i * istride;
+#pragma unroll
+        for (int l = 0; l < W; l += 2) {
+            const double2 gg = *reinterpret_cast<const double2 *>(gi + l);
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                acc[qq][l] = fma(li[qq], gg.x, acc[qq][l]);
+                acc[qq][l + 1] = fma(li[qq], gg.y, acc[qq][l + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < W; ++l)
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) y[qq] = fma(acc[qq][l], vR[(l * QPT + qq) * vstride], y[qq]);
+}
+
+template <int QPT>
+__device__ __forceinline__ void tt_coeff_row(const double *__restrict__ gj, int rp, int istride,
+                                             int r_in, const double *vL, const double *vR,
+                                             int vstride, double (&y)[QPT]) {
+    for (int l0 = 0; l0 < rp; l0 += TT_LCMAX) {
+        const int w = min(TT_LCMAX, rp - l0);
+        const double *gc = gj + l0;
+        const double *vr = vR + (size_t)l0 * QPT * vstride;
+        switch (w) {
+            case 2: tt_coeff_chunk<2, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            case 4: tt_coeff_chunk<4, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            case 6: tt_coeff_chunk<6, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            case 8: tt_coeff_chunk<8, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            case 10: tt_coeff_chunk<10, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            case 12: tt_coeff_chunk<12, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            case 14: tt_coeff_chunk<14, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+            default: tt_coeff_chunk<16, QPT>(gc, istride, r_in, vL, vr, vstride, y); break;
+        }
+    }
+}
+
+template <int QPT, int MODE>
+__global__ void __launch_bounds__(TT_THREADS)
+tt_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__ TTSharedProgram prog,
+                    const double *__restrict__ cores, const double *__restrict__ pts, int64_t N,
+                    double *__restrict__ out, int pingpong) {
+    extern __shared__ __align__(16) double smem[];
+    const TTSharedSmem L = tt_shared_smem_layout(P, MODE, pingpong, QPT, blockDim.x);
+    const int tid = threadIdx.x;
+    const int vstride = blockDim.x;
+    const int D = P.D, G = prog.G;
+    if (MODE == TT_RESIDENT) {
+        const double2 *src = reinterpret_cast<const double2 *>(cores);
+        double2 *dst = reinterpret_cast<double2 *>(smem + L.cores);
+        for (int e = tid; e < (P.total + P.totalT) / 2; e += vstride) dst[e] = src[e];
+        __syncthreads();
+    }
+    const int vsz = P.rmaxp * QPT * vstride;
+    const int tile_rows = vstride * QPT;
+    const int64_t ntiles = (N + tile_rows - 1) / tile_rows;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t q0 = tile * tile_rows;
+        // rows of this thread's query slots (tail: clamp, results are not stored)
+        const double *xrow[QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            int64_t q = q0 + qq * vstride + tid;
+            if (q >= N) q = N - 1;
+            xrow[qq] = pts + q * D;
+        }
+        double *vL = smem + L.v + tid;
+        double *vR = vL + vsz;
+        double *vT = pingpong ? vR + vsz : nullptr;
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) vL[qq * vstride] = 1.0;
+        int lpos = 0;  // vL holds the left product over dims [0, lpos)
+        for (int t = 0; t < prog.n_slots; ++t) {
+            const int a = prog.slot_dim[t];
+            double s[QPT];
+            // ---- right sweep: vR = M_{a+1} ... M_{D-1} (applied right to left) --------------
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) vR[qq * vstride] = 1.0;
+            for (int k = D - 1; k > a; --k) {
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq)
+                    s[qq] = tt_scale(__ldg(xrow[qq] + P.perm[k]), P.lo[k], P.hi[k]);
+                const double *g = tt_core_ptr<MODE>(cores, smem, L.cores, P.offT[k],
+                                                    P.r[k + 1] * P.n[k] * P.rpT[k]);
+                double *vo = pingpong ? vT : vR;
+                tt_apply_core<QPT>(g, P.rpT[k], P.r[k + 1], P.n[k], vR, vo, vstride, s);
+                if (pingpong) {
+                    vT = vR;
+                    vR = vo;
+                }
+            }
+            // ---- left sweep continues up to a ---------------------------------------------------
+            for (int k = lpos; k < a; ++k) {
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq)
+                    s[qq] = tt_scale(__ldg(xrow[qq] + P.perm[k]), P.lo[k], P.hi[k]);
+                const double *g = tt_core_ptr<MODE>(cores, smem, L.cores, P.off[k],
+                                                    P.r[k] * P.n[k] * P.rp[k]);
+                double *vo = pingpong ? vT : vL;
+                tt_apply_core<QPT>(g, P.rp[k], P.r[k], P.n[k], vL, vo, vstride, s);
+                if (pingpong) {
+                    vT = vL;
+                    vL = vo;
+                }
+            }
+            lpos = a;
+            // ---- stencil abscissae of dim a (reference _fd_step / _nudge_point) ---------------
+            const double lo = P.lo[a], hi = P.hi[a];
+            const double h = (hi - lo) * 1e-4;
+            double tc[4][QPT], tn[4][QPT], tw[4][QPT], f[4][QPT];
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                const double x = __ldg(xrow[qq] + P.perm[a]);
+                const double c = tt_nudge(x, lo, hi, h);
+                const double sm[4] = {tt_scale(x, lo, hi), tt_scale(c, lo, hi),
+                                      tt_scale(c + h, lo, hi), tt_scale(c - h, lo, hi)};
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    tc[m][qq] = 1.0;
+                    tn[m][qq] = sm[m];
+                    tw[m][qq] = 2.0 * sm[m];
+                    f[m][qq] = 0.0;
+                }
+            }
+            // ---- coefficient pass: y_j = L . G_a[:, j, :] . R, f_m += y_j T_j(s_m) -------------
+            const double *ga = tt_core_ptr<MODE>(cores, smem, L.cores, P.off[a],
+                                                 P.r[a] * P.n[a] * P.rp[a]);
+            const int rp = P.rp[a], na = P.n[a];
+            for (int j = 0; j < na; ++j) {
+                double y[QPT];
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) y[qq] = 0.0;
+                tt_coeff_row<QPT>(ga + (size_t)j * rp, rp, na * rp, P.r[a], vL, vR, vstride, y);
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int qq = 0; qq < QPT; ++qq) {
+                        f[m][qq] = fma(y[qq], tc[m][qq], f[m][qq]);
+                        const double t2 = fma(tw[m][qq], tn[m][qq], -tc[m][qq]);
+                        tc[m][qq] = tn[m][qq];
+                        tn[m][qq] = t2;
+                    }
+            }
+            // ---- outputs owned by this slot --------------------------------------------------------
+            for (int g = 0; g < G; ++g) {
+                const int rs = prog.row_slot[g];
+                if (!(rs == t || (rs < 0 && t == 0))) continue;
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) {
+                    double res;
+                    if (rs < 0)
+                        res = f[0][qq];
+                    else
+                        res = tt_fd_reduce(prog.row_ord[g], f[2][qq], f[1][qq], f[3][qq], h);
+                    const int64_t q = q0 + qq * vstride + tid;
+                    if (q < N) out[q * G + g] = res;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 
@@ -455,15 +694,31 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
     P.maxcore = maxcore;
     P.rmaxp = rmaxp;
 
-    // pack: [i][j][l] with l padded to even by zeros
-    std::vector<double> packed((size_t)off, 0.0);
+    // transposed copies for right-to-left sweeps: [l][j][i] with i padded to even by zeros
+    int offT = off;
+    for (int k = 0; k < D; ++k) {
+        P.rpT[k] = round_up(ranks[k], 2);
+        P.offT[k] = offT;
+        const int sz = ranks[k + 1] * n[k] * P.rpT[k];
+        offT += sz;
+        if (sz > maxcore) maxcore = sz;
+    }
+    P.totalT = offT - off;
+    P.maxcore = maxcore;
+
+    // pack: forward [i][j][l] with l padded to even by zeros, then transposed [l][j][i]
+    std::vector<double> packed((size_t)offT, 0.0);
     size_t src = 0;
     for (int k = 0; k < D; ++k) {
         const int r0 = ranks[k], r1 = ranks[k + 1];
         for (int i = 0; i < r0; ++i)
             for (int j = 0; j < n[k]; ++j) {
                 double *dst = &packed[(size_t)P.off[k] + ((size_t)i * n[k] + j) * P.rp[k]];
-                for (int l = 0; l < r1; ++l) dst[l] = cores_cat[src++];
+                for (int l = 0; l < r1; ++l) {
+                    const double v = cores_cat[src++];
+                    dst[l] = v;
+                    packed[(size_t)P.offT[k] + ((size_t)l * n[k] + j) * P.rpT[k] + i] = v;
+                }
             }
     }
     // placement of the cores: resident in smem if they fit beside one-slot chain vectors
@@ -474,6 +729,15 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
             pl->mode = TT_STREAM;
             L = tt_smem_layout(P, TT_STREAM, pl->pingpong, 1, TT_THREADS);
             if ((size_t)L.total * 8 > (size_t)pl->smem_optin) pl->mode = TT_GLOBAL;
+        }
+    }
+    pl->mode_shared = TT_RESIDENT;
+    {
+        TTSharedSmem L = tt_shared_smem_layout(P, TT_RESIDENT, pl->pingpong, 1, TT_THREADS);
+        if ((size_t)L.total * 8 > (size_t)pl->smem_optin) {
+            pl->mode_shared = TT_STREAM;
+            L = tt_shared_smem_layout(P, TT_STREAM, pl->pingpong, 1, TT_THREADS);
+            if ((size_t)L.total * 8 > (size_t)pl->smem_optin) pl->mode_shared = TT_GLOBAL;
         }
     }
     DeviceGuard guard(dev);
@@ -557,20 +821,101 @@ static int tt_build_program(const TTPlan *pl, int G, const int32_t *orders, TTFd
     return PCB_OK;
 }
 
+// Rows that differentiate at most one dim each can share partial products (algo 2).
+static bool tt_build_shared_program(const TTFdProgram &prog, TTSharedProgram *sp) {
+    sp->G = prog.G;
+    sp->n_slots = 0;
+    bool used[PCB_MAX_DIMS] = {false};
+    for (int g = 0; g < prog.G; ++g) {
+        if (prog.row[g].m > 1) return false;
+        if (prog.row[g].m == 1) used[prog.row[g].dim[0]] = true;
+    }
+    int slot_of[PCB_MAX_DIMS];
+    for (int k = 0; k < PCB_MAX_DIMS; ++k) {
+        slot_of[k] = -1;
+        if (used[k]) {
+            slot_of[k] = sp->n_slots;
+            sp->slot_dim[sp->n_slots++] = k;
+        }
+    }
+    if (sp->n_slots == 0) return false;  // values only: nothing to share
+    for (int g = 0; g < prog.G; ++g) {
+        sp->row_slot[g] = prog.row[g].m == 1 ? slot_of[prog.row[g].dim[0]] : -1;
+        sp->row_ord[g] = prog.row[g].m == 1 ? prog.row[g].ord[0] : 0;
+    }
+    return true;
+}
+
+template <int QPT, int MODE>
+static int tt_launch_shared(const TTPlan *pl, const TTSharedProgram &sp, const double *d_points,
+                            int64_t N, double *d_out, cudaStream_t st) {
+    const TTSharedSmem L = tt_shared_smem_layout(pl->P, MODE, pl->pingpong, QPT, TT_THREADS);
+    const size_t smem = (size_t)L.total * sizeof(double);
+    auto kernel = tt_fd_shared_kernel<QPT, MODE>;
+    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TT_THREADS, smem));
+    if (per_sm < 1) return fail(PCB_ECUDA, "TT shared-FD kernel does not fit on an SM");
+    const int64_t ntiles = (N + (int64_t)TT_THREADS * QPT - 1) / ((int64_t)TT_THREADS * QPT);
+    const int64_t cap = (int64_t)pl->sm_count * per_sm;
+    kernel<<<(int)(ntiles < cap ? ntiles : cap), TT_THREADS, smem, st>>>(pl->P, sp, pl->d_cores,
+                                                                        d_points, N, d_out,
+                                                                        pl->pingpong);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}
+
+static int tt_shared_qpt(const TTPlan *pl) {
+    const TTSharedSmem L2 = tt_shared_smem_layout(pl->P, pl->mode_shared, pl->pingpong, 2, TT_THREADS);
+    return (size_t)L2.total * sizeof(double) <= (size_t)pl->smem_optin ? 2 : 1;
+}
+
+// Which algorithm pcb_tt_eval_fd(algo = 0) runs for these rows: 1 or 2 (negative on error).
+extern "C" PCB_API int pcb_tt_fd_algo(void *plan, int G, const int32_t *orders) {
+    TTPlan *pl = static_cast<TTPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_TT, "not a TT plan");
+    PCB_REQUIRE(orders, "null orders");
+    TTFdProgram prog;
+    int max_active = 0;
+    if (int rc = tt_build_program(pl, G, orders, &prog, &max_active)) return rc;
+    TTSharedProgram sp;
+    return tt_build_shared_program(prog, &sp) ? 2 : 1;
+}
+
 extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G,
-                              const int32_t *orders, double *d_out, int algo, void *stream) {
+                                      const int32_t *orders, double *d_out, int algo, void *stream) {
     TTPlan *pl = static_cast<TTPlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_TT, "not a TT plan");
     PCB_REQUIRE(orders, "null orders");
     PCB_REQUIRE(N >= 0, "negative N");
+    PCB_REQUIRE(algo >= 0 && algo <= 2, "algo %d not available", algo);
     TTFdProgram prog;
     int max_active = 0;
     if (int rc = tt_build_program(pl, G, orders, &prog, &max_active)) return rc;
+    TTSharedProgram sp;
+    const bool can_share = tt_build_shared_program(prog, &sp);
+    if (algo == 2 && !can_share)
+        return fail(PCB_EUNSUPPORTED, "algo 2 needs at least one differentiated dim and at most "
+                    "one per row");
     if (N == 0) return PCB_OK;
     PCB_REQUIRE(d_points && d_out, "null device pointer");
-    PCB_REQUIRE(algo == 0 || algo == 1, "algo %d not available", algo);
     DeviceGuard guard(pl->dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (algo == 2 || (algo == 0 && can_share)) {
+        const int qpt = tt_shared_qpt(pl);
+        switch (pl->mode_shared) {
+            case TT_RESIDENT:
+                return qpt == 2 ? tt_launch_shared<2, TT_RESIDENT>(pl, sp, d_points, N, d_out, st)
+                                : tt_launch_shared<1, TT_RESIDENT>(pl, sp, d_points, N, d_out, st);
+            case TT_STREAM:
+                return qpt == 2 ? tt_launch_shared<2, TT_STREAM>(pl, sp, d_points, N, d_out, st)
+                                : tt_launch_shared<1, TT_STREAM>(pl, sp, d_points, N, d_out, st);
+            default:
+                return qpt == 2 ? tt_launch_shared<2, TT_GLOBAL>(pl, sp, d_points, N, d_out, st)
+                                : tt_launch_shared<1, TT_GLOBAL>(pl, sp, d_points, N, d_out, st);
+        }
+    }
     if (tt_pick_qpt(pl) == 2)
         TT_LAUNCH_BY_MODE(tt_fd_general_kernel, 2, pl->P, prog, pl->d_cores, d_points, N, d_out,
                           pl->pingpong);

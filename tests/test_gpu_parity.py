@@ -61,10 +61,18 @@ def test_tt_device_resident_matches_host_path(name):
 
 
 @pytest.mark.parametrize("name", TT_CASES)
-def test_tt_fd_greeks_match_reference(name):
+@pytest.mark.parametrize("algo", [1, 2, 0])
+def test_tt_fd_greeks_match_reference(name, algo):
+    """algo 1: one chain per stencil point (any rows); algo 2: shared partial products (rows that
+    differentiate at most one dim); algo 0: the library's own choice."""
     g, tt = _tt(name)
     cores, domain, dim_order = G.tt_parts(g)
-    got = tt.eval_multi_batch(g["fd_points"], g["fd_orders"], algo=1)
+    if algo == 2:
+        keep = np.array([int((o > 0).sum()) <= 1 for o in g["fd_orders"]])
+        g = dict(g, fd_orders=g["fd_orders"][keep], fd_values=g["fd_values"][:, keep])
+        with pytest.raises(NotImplementedError):
+            tt.eval_multi_batch(g["fd_points"][:4], [[1] * tt.num_dimensions], algo=2)
+    got = tt.eval_multi_batch(g["fd_points"], g["fd_orders"], algo=algo)
     ref = g["fd_values"]
     assert got.shape == ref.shape
     tol = G.fd_tolerance(g, domain, dim_order)
