@@ -146,7 +146,8 @@ PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, doubl
 
 /* ---------------------------------------------------------------------------------------------
  * Roofline probes (bench.py): measured FP64 pipe peaks of the device, in TFLOP/s.
- *   kind 0 = DFMA (register-resident FMA chains), 1 = DMMA (mma.sync m8n8k4 f64)
+ *   kind 0 = DFMA (register-resident FMA chains), 1 = DMMA (mma.sync m8n8k4 f64),
+ *   kind 2 = both interleaved in every warp (sum of the two flop counts)
  * ------------------------------------------------------------------------------------------ */
 PCB_API int pcb_probe_fp64_peak(int dev, int kind, double *tflops, double *ms);
 

@@ -72,6 +72,32 @@ __global__ void __launch_bounds__(256) probe_dmma_kernel(double *out, double see
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Both at once: 8 DMMA + 8 DFMA per iteration in every warp.  If the FP64 tensor sub-pipe and the
+// FP64 FMA pipe are separate, this runs faster than the sum of the two alone.
+__global__ void __launch_bounds__(256) probe_mixed_kernel(double *out, double seed) {
+    double c[8][2], a8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c[i][0] = c[i][1] = 0.0;
+        a8[i] = seed + i + threadIdx.x;
+    }
+    const double a = seed + (threadIdx.x & 31) * 1e-3, b = 1e-3 * (threadIdx.x & 7);
+    const double m = 1.0000001, k = 1e-9;
+    for (int it = 0; it < PROBE_ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+            a8[i] = fma(a8[i], m, k);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + a8[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace pcb
 
 using namespace pcb;
@@ -108,7 +134,7 @@ extern "C" PCB_API int pcb_plan_destroy(void *plan) {
 
 extern "C" PCB_API int pcb_probe_fp64_peak(int dev, int kind, double *tflops, double *ms) {
     PCB_REQUIRE(tflops && ms, "null argument");
-    PCB_REQUIRE(kind == 0 || kind == 1, "probe kind %d unknown", kind);
+    PCB_REQUIRE(kind >= 0 && kind <= 2, "probe kind %d unknown", kind);
     int sm = 0, smem = 0, cc = 0;
     if (int rc = device_props(dev, &sm, &smem, &cc)) return rc;
     DeviceGuard guard(dev);
@@ -123,8 +149,10 @@ extern "C" PCB_API int pcb_probe_fp64_peak(int dev, int kind, double *tflops, do
         cudaEventRecord(e0);
         if (kind == 0)
             probe_dfma_kernel<<<blocks, threads>>>(buf, 1.0 + rep);
-        else
+        else if (kind == 1)
             probe_dmma_kernel<<<blocks, threads>>>(buf, 1.0 + rep);
+        else
+            probe_mixed_kernel<<<blocks, threads>>>(buf, 1.0 + rep);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float t = 0.f;
@@ -138,8 +166,9 @@ extern "C" PCB_API int pcb_probe_fp64_peak(int dev, int kind, double *tflops, do
     PCB_CUDA(cudaGetLastError());
     const double total_threads = (double)blocks * threads;
     // DFMA: 8 FMA per thread per iteration; DMMA: 8 MMAs per warp per iteration, 8*8*4 FMA each
-    const double fma = kind == 0 ? total_threads * 8.0 * PROBE_ITERS
-                                 : (total_threads / 32.0) * 8.0 * 256.0 * PROBE_ITERS;
+    const double fma_dfma = total_threads * 8.0 * PROBE_ITERS;
+    const double fma_dmma = (total_threads / 32.0) * 8.0 * 256.0 * PROBE_ITERS;
+    const double fma = kind == 0 ? fma_dfma : (kind == 1 ? fma_dmma : fma_dfma + fma_dmma);
     *ms = best;
     *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
     return PCB_OK;

@@ -1,0 +1,243 @@
+// ChebyshevTT: plan creation, launch-configuration choice and the C-ABI entry points.
+#include <cstdlib>
+
+#include "pcb_tt.cuh"
+
+namespace pcb {
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+static bool tt_try_cfg(const TTPlan *pl, bool shared, int mode, int qpt, int threads, TTCfg *c) {
+    const TTParams &P = pl->P;
+    const int lc = mode == TT_RESIDENT ? (P.rmaxp <= 8 ? 8 : (P.rmaxp <= 12 ? 12 : 16)) : 16;
+    int pingpong = 0;
+    for (int k = 0; k < P.D; ++k)
+        if (P.rp[k] > lc || P.rpT[k] > lc) pingpong = 1;
+    const int nbuf = (shared ? 2 : 1) + pingpong;
+    const size_t bytes = (size_t)tt_smem_doubles(P, mode, shared, nbuf, qpt, threads) * sizeof(double);
+    if (bytes > (size_t)pl->smem_optin) return false;
+    // three/four query slots per thread are instantiated for the 12-wide resident case only
+    if (qpt >= 3 && !(mode == TT_RESIDENT && lc == 12)) return false;
+    c->qpt = qpt;
+    c->threads = threads;
+    c->lc = lc;
+    c->mode = mode;
+    c->pingpong = pingpong;
+    c->smem = bytes;
+    return true;
+}
+
+// Preference: cores resident in shared memory, two query slots per thread (halves the LDS
+// traffic per DFMA), as many threads as the register file allows for that kernel.
+int tt_pick_cfg(const TTPlan *pl, bool shared, TTCfg *cfg) {
+    const int force_q = env_int("PCB_TT_QPT", 0), force_t = env_int("PCB_TT_THREADS", 0);
+    // measured on B200 (tools/tt_sweep.py, 5D Black-Scholes TT): chain kernels 3 slots x 256
+    // threads 2.75e9 values/s vs 2.51e9 for 2 x 512; shared-FD kernel 2 x 384 best (1.14e9 q/s)
+    static const int chain_pref[][2] = {{3, 256}, {2, 512}, {2, 256}, {1, 512}, {1, 256}};
+    static const int shared_pref[][2] = {{2, 384}, {2, 256}, {1, 512}, {1, 256}, {1, 128}};
+    for (int mode = TT_RESIDENT; mode <= TT_GLOBAL; ++mode) {
+        if (force_q || force_t) {
+            const int q = force_q ? force_q : 2, t = force_t ? force_t : 256;
+            if (tt_try_cfg(pl, shared, mode, q, t, cfg)) return PCB_OK;
+            continue;
+        }
+        for (int i = 0; i < 5; ++i) {
+            const int *p = shared ? shared_pref[i] : chain_pref[i];
+            if (tt_try_cfg(pl, shared, mode, p[0], p[1], cfg)) return PCB_OK;
+        }
+    }
+    return fail(PCB_EUNSUPPORTED, "TT plan does not fit in shared memory in any configuration");
+}
+
+static int tt_build_program(const TTPlan *pl, int G, const int32_t *orders, TTFdProgram *prog) {
+    const TTParams &P = pl->P;
+    PCB_REQUIRE(G >= 1 && G <= TT_MAX_G, "number of derivative rows %d outside [1, %d]", G, TT_MAX_G);
+    prog->G = G;
+    for (int g = 0; g < G; ++g) {
+        TTFdRow &row = prog->row[g];
+        row.m = 0;
+        for (int k = 0; k < P.D; ++k) {  // storage frame: order of storage dim k is orders[g][perm[k]]
+            const int o = orders[(size_t)g * P.D + P.perm[k]];
+            PCB_REQUIRE(o >= 0, "negative derivative order");
+            if (o == 0) continue;
+            // reference: ValueError(f"Derivative order {order} not supported (use 1 or 2)")
+            PCB_REQUIRE(o <= 2, "Derivative order %d not supported (use 1 or 2)", o);
+            if (row.m == TT_MAX_ACTIVE)
+                return fail(PCB_EUNSUPPORTED,
+                            "finite-difference rows with more than %d differentiated dims are not "
+                            "supported on the device", TT_MAX_ACTIVE);
+            row.dim[row.m] = k;
+            row.ord[row.m] = o;
+            ++row.m;
+        }
+    }
+    return PCB_OK;
+}
+
+// Rows that differentiate at most one dim each can share partial products (algo 2).
+static bool tt_build_shared_program(const TTFdProgram &prog, TTSharedProgram *sp) {
+    sp->G = prog.G;
+    sp->n_slots = 0;
+    bool used[PCB_MAX_DIMS] = {false};
+    for (int g = 0; g < prog.G; ++g) {
+        if (prog.row[g].m > 1) return false;
+        if (prog.row[g].m == 1) used[prog.row[g].dim[0]] = true;
+    }
+    int slot_of[PCB_MAX_DIMS];
+    for (int k = 0; k < PCB_MAX_DIMS; ++k) {
+        slot_of[k] = -1;
+        if (used[k]) {
+            slot_of[k] = sp->n_slots;
+            sp->slot_dim[sp->n_slots++] = k;
+        }
+    }
+    if (sp->n_slots == 0) return false;  // values only: nothing to share
+    for (int g = 0; g < prog.G; ++g) {
+        sp->row_slot[g] = prog.row[g].m == 1 ? slot_of[prog.row[g].dim[0]] : -1;
+        sp->row_ord[g] = prog.row[g].m == 1 ? prog.row[g].ord[0] : 0;
+    }
+    return true;
+}
+
+}  // namespace pcb
+
+using namespace pcb;
+
+extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, const int32_t *ranks,
+                                          const double *lo, const double *hi,
+                                          const int32_t *dim_order, const double *cores_cat,
+                                          void **plan) {
+    PCB_REQUIRE(plan && n && ranks && lo && hi && cores_cat, "null argument");
+    PCB_REQUIRE(D >= 1 && D <= PCB_MAX_DIMS, "num_dimensions %d outside [1, %d]", D, PCB_MAX_DIMS);
+    PCB_REQUIRE(ranks[0] == 1 && ranks[D] == 1, "boundary TT ranks must be 1");
+    TTPlan *pl = new TTPlan();
+    pl->kind = PLAN_TT;
+    pl->dev = dev;
+    int cc = 0;
+    if (int rc = device_props(dev, &pl->sm_count, &pl->smem_optin, &cc)) {
+        delete pl;
+        return rc;
+    }
+    TTParams &P = pl->P;
+    memset(&P, 0, sizeof(P));
+    P.D = D;
+    std::vector<char> seen(D, 0);
+    int off = 0, rmaxp = 2, maxcore = 0;
+    for (int k = 0; k < D; ++k) {
+        const int perm = dim_order ? dim_order[k] : k;
+        if (n[k] < 1 || ranks[k] < 1 || ranks[k + 1] < 1 || perm < 0 || perm >= D || seen[perm] ||
+            !(lo[k] < hi[k])) {
+            delete pl;
+            return fail(PCB_EINVAL, "invalid TT description at storage dim %d", k);
+        }
+        seen[perm] = 1;
+        P.n[k] = n[k];
+        P.r[k] = ranks[k];
+        P.rp[k] = round_up(ranks[k + 1], 2);
+        P.rpT[k] = round_up(ranks[k], 2);
+        P.off[k] = off;
+        P.perm[k] = perm;
+        P.lo[k] = lo[k];
+        P.hi[k] = hi[k];
+        const int sz = ranks[k] * n[k] * P.rp[k];
+        off += sz;
+        if (sz > maxcore) maxcore = sz;
+        if (P.rp[k] > rmaxp) rmaxp = P.rp[k];
+        if (P.rpT[k] > rmaxp) rmaxp = P.rpT[k];
+    }
+    P.r[D] = 1;
+    P.total = off;
+    P.rmaxp = rmaxp;
+    // transposed copies for right-to-left sweeps: [l][j][i] with i padded to even by zeros
+    int offT = off;
+    for (int k = 0; k < D; ++k) {
+        P.offT[k] = offT;
+        const int sz = ranks[k + 1] * n[k] * P.rpT[k];
+        offT += sz;
+        if (sz > maxcore) maxcore = sz;
+    }
+    P.totalT = offT - off;
+    P.maxcore = maxcore;
+
+    std::vector<double> packed((size_t)offT, 0.0);
+    size_t src = 0;
+    for (int k = 0; k < D; ++k) {
+        const int r0 = ranks[k], r1 = ranks[k + 1];
+        for (int i = 0; i < r0; ++i)
+            for (int j = 0; j < n[k]; ++j) {
+                double *dst = &packed[(size_t)P.off[k] + ((size_t)i * n[k] + j) * P.rp[k]];
+                for (int l = 0; l < r1; ++l) {
+                    const double v = cores_cat[src++];
+                    dst[l] = v;
+                    packed[(size_t)P.offT[k] + ((size_t)l * n[k] + j) * P.rpT[k] + i] = v;
+                }
+            }
+    }
+    if (int rc = tt_pick_cfg(pl, false, &pl->cfg_chain)) {
+        delete pl;
+        return rc;
+    }
+    if (int rc = tt_pick_cfg(pl, true, &pl->cfg_shared)) {
+        delete pl;
+        return rc;
+    }
+    DeviceGuard guard(dev);
+    if (!guard.ok || cudaMalloc(&pl->d_cores, packed.size() * sizeof(double)) != cudaSuccess) {
+        delete pl;
+        return fail(PCB_ENOMEM, "cudaMalloc of %zu B for TT cores failed on device %d",
+                    packed.size() * sizeof(double), dev);
+    }
+    if (cudaMemcpy(pl->d_cores, packed.data(), packed.size() * sizeof(double),
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete pl;
+        return fail(PCB_ECUDA, "upload of TT cores failed");
+    }
+    *plan = pl;
+    return PCB_OK;
+}
+
+extern "C" PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N, double *d_out,
+                                   void *stream) {
+    TTPlan *pl = static_cast<TTPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_TT, "not a TT plan");
+    PCB_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return PCB_OK;
+    PCB_REQUIRE(d_points && d_out, "null device pointer");
+    DeviceGuard guard(pl->dev);
+    return tt_launch_value(pl, d_points, N, d_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" PCB_API int pcb_tt_fd_algo(void *plan, int G, const int32_t *orders) {
+    TTPlan *pl = static_cast<TTPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_TT, "not a TT plan");
+    PCB_REQUIRE(orders, "null orders");
+    TTFdProgram prog;
+    if (int rc = tt_build_program(pl, G, orders, &prog)) return rc;
+    TTSharedProgram sp;
+    return tt_build_shared_program(prog, &sp) ? 2 : 1;
+}
+
+extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G,
+                                      const int32_t *orders, double *d_out, int algo, void *stream) {
+    TTPlan *pl = static_cast<TTPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_TT, "not a TT plan");
+    PCB_REQUIRE(orders, "null orders");
+    PCB_REQUIRE(N >= 0, "negative N");
+    PCB_REQUIRE(algo >= 0 && algo <= 2, "algo %d not available", algo);
+    TTFdProgram prog;
+    if (int rc = tt_build_program(pl, G, orders, &prog)) return rc;
+    TTSharedProgram sp;
+    const bool can_share = tt_build_shared_program(prog, &sp);
+    if (algo == 2 && !can_share)
+        return fail(PCB_EUNSUPPORTED, "algo 2 needs at least one differentiated dim and at most "
+                    "one per row");
+    if (N == 0) return PCB_OK;
+    PCB_REQUIRE(d_points && d_out, "null device pointer");
+    DeviceGuard guard(pl->dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (algo == 2 || (algo == 0 && can_share)) return tt_launch_shared(pl, sp, d_points, N, d_out, st);
+    return tt_launch_general(pl, prog, d_points, N, d_out, st);
+}
