@@ -136,6 +136,17 @@ __device__ __forceinline__ void tt_chunk(const double *__restrict__ g, int rp, i
 #pragma unroll
         for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
     }
+    // Software pipeline over the rows (i, j) of the chunk, which are contiguous in memory with
+    // stride rp: the 128-bit loads of row t+1 are issued before the FMAs of row t so that LDS and
+    // DFMA issue slots interleave.  Rows are zero-padded to an even stride, so every 128-bit load
+    // is in bounds; an odd W simply skips the FMA on the pad column.  The load after the last row
+    // reads (and discards) the doubles that follow the core, which always exist (next core /
+    // chain vectors in shared memory, allocation padding in global memory).
+    constexpr int H = (W + 1) / 2;
+    const double *gp = g;
+    double2 gcur[H];
+#pragma unroll
+    for (int l = 0; l < H; ++l) gcur[l] = *reinterpret_cast<const double2 *>(gp + 2 * l);
     for (int i = 0; i < r_in; ++i) {
         double c0[QPT], c1[QPT];
 #pragma unroll
@@ -144,18 +155,18 @@ __device__ __forceinline__ void tt_chunk(const double *__restrict__ g, int rp, i
             c0[qq] = vi;          // v[i] * T_0
             c1[qq] = vi * s[qq];  // v[i] * T_1
         }
-        const double *gi = g + (size_t)i * n * rp;
 #pragma unroll 2
         for (int j = 0; j < n; ++j) {
+            gp += rp;
+            double2 gnext[H];
 #pragma unroll
-            for (int l = 0; l < W; l += 2) {
-                // rows are zero-padded to an even stride, so the 128-bit load is always in bounds;
-                // an odd W simply skips the FMA on the pad column
-                const double2 gg = *reinterpret_cast<const double2 *>(gi + l);
+            for (int l = 0; l < H; ++l) gnext[l] = *reinterpret_cast<const double2 *>(gp + 2 * l);
+#pragma unroll
+            for (int l = 0; l < H; ++l) {
 #pragma unroll
                 for (int qq = 0; qq < QPT; ++qq) {
-                    acc[qq][l] = fma(c0[qq], gg.x, acc[qq][l]);
-                    if (l + 1 < W) acc[qq][l + 1] = fma(c0[qq], gg.y, acc[qq][l + 1]);
+                    acc[qq][2 * l] = fma(c0[qq], gcur[l].x, acc[qq][2 * l]);
+                    if (2 * l + 1 < W) acc[qq][2 * l + 1] = fma(c0[qq], gcur[l].y, acc[qq][2 * l + 1]);
                 }
             }
 #pragma unroll
@@ -164,7 +175,8 @@ __device__ __forceinline__ void tt_chunk(const double *__restrict__ g, int rp, i
                 c0[qq] = c1[qq];
                 c1[qq] = c2;
             }
-            gi += rp;
+#pragma unroll
+            for (int l = 0; l < H; ++l) gcur[l] = gnext[l];
         }
     }
 #pragma unroll

@@ -34,9 +34,10 @@ static bool tt_try_cfg(const TTPlan *pl, bool shared, int mode, int qpt, int thr
 // traffic per DFMA), as many threads as the register file allows for that kernel.
 int tt_pick_cfg(const TTPlan *pl, bool shared, TTCfg *cfg) {
     const int force_q = env_int("PCB_TT_QPT", 0), force_t = env_int("PCB_TT_THREADS", 0);
-    // measured on B200 (tools/tt_sweep.py, 5D Black-Scholes TT): chain kernels 3 slots x 256
-    // threads 2.75e9 values/s vs 2.51e9 for 2 x 512; shared-FD kernel 2 x 384 best (1.14e9 q/s)
-    static const int chain_pref[][2] = {{3, 256}, {2, 512}, {2, 256}, {1, 512}, {1, 256}};
+    // measured on B200 (tools/tt_sweep.py, 5D Black-Scholes TT, gpurun_out/tt_sweep3.log): chain
+    // kernels 2 slots x 512 threads 3.06e9 values/s (3 x 256: 2.79e9, 1 x 512: 2.29e9);
+    // shared-FD kernel 2 x 384 threads 1.26e9 q/s (2 x 512: 1.02e9, 3 x 256: 1.19e9)
+    static const int chain_pref[][2] = {{2, 512}, {3, 256}, {2, 256}, {1, 512}, {1, 256}};
     static const int shared_pref[][2] = {{2, 384}, {2, 256}, {1, 512}, {1, 256}, {1, 128}};
     for (int mode = TT_RESIDENT; mode <= TT_GLOBAL; ++mode) {
         if (force_q || force_t) {
@@ -162,7 +163,8 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
     P.totalT = offT - off;
     P.maxcore = maxcore;
 
-    std::vector<double> packed((size_t)offT, 0.0);
+    // + one row of slack: the software-pipelined kernels load (and discard) the row after the last
+    std::vector<double> packed((size_t)offT + rmaxp + 32, 0.0);
     size_t src = 0;
     for (int k = 0; k < D; ++k) {
         const int r0 = ranks[k], r1 = ranks[k + 1];

@@ -24,21 +24,31 @@ __device__ __forceinline__ void tt_coeff_chunk(const double *__restrict__ gj, in
     for (int qq = 0; qq < QPT; ++qq)
 #pragma unroll
         for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
+    // software pipeline over i: row i+1 (stride istride) is loaded before the FMAs of row i
+    constexpr int H = (W + 1) / 2;
+    const double *gp = gj;
+    double2 gcur[H];
+#pragma unroll
+    for (int l = 0; l < H; ++l) gcur[l] = *reinterpret_cast<const double2 *>(gp + 2 * l);
 #pragma unroll 2
     for (int i = 0; i < r_in; ++i) {
         double li[QPT];
 #pragma unroll
         for (int qq = 0; qq < QPT; ++qq) li[qq] = vL[(i * QPT + qq) * vstride];
-        const double *gi = gj + (size_t)i * istride;
+        if (i + 1 < r_in) gp += istride;  // the last iteration re-reads its own row
+        double2 gnext[H];
 #pragma unroll
-        for (int l = 0; l < W; l += 2) {
-            const double2 gg = *reinterpret_cast<const double2 *>(gi + l);
+        for (int l = 0; l < H; ++l) gnext[l] = *reinterpret_cast<const double2 *>(gp + 2 * l);
+#pragma unroll
+        for (int l = 0; l < H; ++l) {
 #pragma unroll
             for (int qq = 0; qq < QPT; ++qq) {
-                acc[qq][l] = fma(li[qq], gg.x, acc[qq][l]);
-                if (l + 1 < W) acc[qq][l + 1] = fma(li[qq], gg.y, acc[qq][l + 1]);
+                acc[qq][2 * l] = fma(li[qq], gcur[l].x, acc[qq][2 * l]);
+                if (2 * l + 1 < W) acc[qq][2 * l + 1] = fma(li[qq], gcur[l].y, acc[qq][2 * l + 1]);
             }
         }
+#pragma unroll
+        for (int l = 0; l < H; ++l) gcur[l] = gnext[l];
     }
 #pragma unroll
     for (int l = 0; l < W; ++l)
