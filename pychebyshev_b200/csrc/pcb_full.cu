@@ -255,8 +255,12 @@ full_dmma_kernel(const __grid_constant__ DmmaParams P, const double *__restrict_
                         double acc2[DM_MT][2];
 #pragma unroll
                         for (int mt = 0; mt < DM_MT; ++mt) acc2[mt][0] = acc2[mt][1] = 0.0;
-                        for (int d = 0; d < P.nd; ++d) {
-                            double cf[DM_MT][2];
+                        // d-loop, software pipelined over two accumulator sets: the MMAs of step d
+                        // are issued before the weighted fold of step d-1, so the fold never waits
+                        // on the tensor pipe.
+                        const double *wd_base =
+                            P.dim_d >= 0 ? w_s + (size_t)P.woff[P.dim_d] * DM_QT + qrow : nullptr;
+                        auto mma_step = [&](int d, double (&cf)[DM_MT][2]) {
 #pragma unroll
                             for (int mt = 0; mt < DM_MT; ++mt) cf[mt][0] = cf[mt][1] = 0.0;
 #pragma unroll
@@ -266,8 +270,10 @@ full_dmma_kernel(const __grid_constant__ DmmaParams P, const double *__restrict_
                                 for (int mt = 0; mt < DM_MT; ++mt)
                                     dmma884(cf[mt][0], cf[mt][1], afrag[kb][mt], b);
                             }
-                            if (P.dim_d >= 0) {
-                                const double *wd = w_s + (size_t)(P.woff[P.dim_d] + d) * DM_QT + qrow;
+                        };
+                        auto fold_step = [&](int d, const double (&cf)[DM_MT][2]) {
+                            if (wd_base) {
+                                const double *wd = wd_base + (size_t)d * DM_QT;
 #pragma unroll
                                 for (int mt = 0; mt < DM_MT; ++mt) {
                                     const double w = wd[mt * 8];
@@ -281,6 +287,22 @@ full_dmma_kernel(const __grid_constant__ DmmaParams P, const double *__restrict_
                                     acc2[mt][1] = cf[mt][1];
                                 }
                             }
+                        };
+                        double cfa[DM_MT][2], cfb[DM_MT][2];
+                        mma_step(0, cfa);
+                        int d = 1;
+                        for (; d + 1 < P.nd; d += 2) {
+                            mma_step(d, cfb);
+                            fold_step(d - 1, cfa);
+                            mma_step(d + 1, cfa);
+                            fold_step(d, cfb);
+                        }
+                        if (d < P.nd) {
+                            mma_step(d, cfb);
+                            fold_step(d - 1, cfa);
+                            fold_step(d, cfb);
+                        } else {
+                            fold_step(d - 1, cfa);
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[s]);  // slab consumed by this warp

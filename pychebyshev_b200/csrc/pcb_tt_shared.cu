@@ -142,15 +142,22 @@ tt_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__ 
                 for (int m = 0; m < 4; ++m) b1[m][qq] = b2[m][qq] = 0.0;
             }
             // ---- coefficient pass, j descending; Clenshaw: b_j = y_j + 2 s b_{j+1} - b_{j+2} -----
-            const double *ga = tt_core_ptr<MODE>(cores, smem, P.off[a], P.r[a] * P.n[a] * P.rp[a]);
-            const int rp = P.rp[a], na = P.n[a];
+            // y_j = sum_{i,l} L_i G[i][j][l] R_l is symmetric in (L, i) <-> (R, l): run it over the
+            // layout whose register-accumulated index is the wider one (fewer LDS per DFMA)
+            const bool fwd = P.r[a + 1] >= P.r[a];
+            const int na = P.n[a];
+            const int rp = fwd ? P.rp[a] : P.rpT[a];
+            const int r_acc = fwd ? P.r[a + 1] : P.r[a], r_rows = fwd ? P.r[a] : P.r[a + 1];
+            const double *ga = tt_core_ptr<MODE>(cores, smem, fwd ? P.off[a] : P.offT[a],
+                                                 r_rows * na * rp);
+            const double *v_rows = fwd ? vL : vR, *v_acc = fwd ? vR : vL;
             double y0[QPT];
             for (int j = na - 1; j >= 0; --j) {
                 double y[QPT];
 #pragma unroll
                 for (int qq = 0; qq < QPT; ++qq) y[qq] = 0.0;
-                tt_coeff_row<QPT, LC>(ga + (size_t)j * rp, P.r[a + 1], na * rp, P.r[a], vL, vR, vstride,
-                                      y);
+                tt_coeff_row<QPT, LC>(ga + (size_t)j * rp, r_acc, na * rp, r_rows, v_rows, v_acc,
+                                      vstride, y);
                 if (j > 0) {
 #pragma unroll
                     for (int m = 0; m < 4; ++m)
