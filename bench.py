@@ -352,7 +352,10 @@ def run_ours(args, rank, local_rank, world):
         "roofline": {
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf, "traffic": None,
-            "kernel": "tt_fd_general_kernel" if args.algo == 1 else "tt_fd_shared_kernel",
+            "kernel": ("tt_fd_general_kernel" if args.algo == 1 else
+                       ("ttc_fd_shared_kernel (cores in the constant bank, LDCU -> DFMA)"
+                        if plan.info()["uniform_path_fd"] else "tt_fd_shared_kernel")),
+            "plan": plan.info(),
             "kernel_ms": kernel_ms, "flop_per_query": flop_q, "flop_model": flop_note,
             "peak_source": "measured live: pcb_probe_fp64_peak DFMA register-chain kernel "
                            f"(DMMA m8n8k4 probe: {peak_dmma:.1f} TFLOP/s); MEASURED_PEAKS.json "

@@ -76,6 +76,12 @@ PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N, double *d
 PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G, const int32_t *orders,
                    double *d_out, int algo, void *stream);
 
+/* How the plan will be evaluated (reporting only): out8 = { values on the uniform-datapath
+ * (constant bank) kernels?, shared-FD on them?, query slots per thread, threads (values), threads
+ * (shared-FD), core placement of the shared-memory kernels (0 resident, 1 streamed, 2 global),
+ * their slots per thread, their threads }. */
+PCB_API int pcb_tt_plan_info(void *plan, int32_t *out8);
+
 /* Which algorithm pcb_tt_eval_fd(algo = 0) runs for these rows: 1 or 2; negative PCB_E* on error. */
 PCB_API int pcb_tt_fd_algo(void *plan, int G, const int32_t *orders);
 

@@ -253,6 +253,15 @@ class TTPlan(DevicePlan):
         view.algo = algo
         return view
 
+    def info(self) -> dict:
+        """Which kernels evaluate this plan (reporting only)."""
+        handle = self._handle if self._handle else self._owner._handle
+        out = (C.c_int32 * 8)()
+        _lib.check(_lib.load().pcb_tt_plan_info(handle, out))
+        keys = ("uniform_path_values", "uniform_path_fd", "uniform_qpt", "uniform_threads_values",
+                "uniform_threads_fd", "smem_core_placement", "smem_fd_qpt", "smem_fd_threads")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def resolved_algo(self) -> int:
         """The algorithm ``pcb_tt_eval_fd`` runs for this view's rows (1 or 2)."""
         if self._orders is None:

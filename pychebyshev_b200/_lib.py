@@ -37,6 +37,7 @@ SIGNATURES = {
     "pcb_tt_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pcb_tt_eval_fd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, _i32p, C.c_void_p,
                                  C.c_int, C.c_void_p]),
+    "pcb_tt_plan_info": (C.c_int, [C.c_void_p, _i32p]),
     "pcb_tt_fd_algo": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
     "pcb_full_plan_create": (C.c_int, [C.c_int, C.c_int, _i32p, _f64p, _f64p, C.c_int,
                                        C.POINTER(_f64p), _vpp]),

@@ -36,9 +36,16 @@ struct TTParams {
     int rpT[PCB_MAX_DIMS];   // r[k] rounded up to even: row stride of transposed core k [l][j][rpT]
     int offT[PCB_MAX_DIMS];  // offset (doubles, from the buffer start) of transposed core k
     int perm[PCB_MAX_DIMS];  // storage position k -> user column
+    int coff[PCB_MAX_DIMS];   // constant bank: offset of unpadded forward core k  [i][j][r_k+1]
+    int coffT[PCB_MAX_DIMS];  // constant bank: offset of unpadded transposed core k [l][j][r_k]
     double lo[PCB_MAX_DIMS];
     double hi[PCB_MAX_DIMS];
 };
+
+// Uniform-datapath kernels (pcb_tt_const.cu) read the cores of the resident plan from the 64 KB
+// __constant__ bank.
+constexpr int TT_CONST_MAX = 8192;
+constexpr int TT_CONST_MAX_RANK = 16;
 
 // One output row of pcb_tt_eval_fd, storage frame.
 struct TTFdRow {
@@ -72,9 +79,13 @@ struct TTPlan : PlanBase {
     double *d_cores = nullptr;
     TTCfg cfg_chain;   // value + general finite-difference kernels
     TTCfg cfg_shared;  // shared partial-product finite-difference kernel
-    ~TTPlan() override {
-        if (d_cores) cudaFree(d_cores);
-    }
+    // uniform-datapath path (cores in the constant bank), when the train is small enough:
+    // values need the forward cores, the shared-FD kernel the transposed copies as well
+    bool const_value_ok = false, const_shared_ok = false;
+    int const_qpt = 2, const_threads_value = 512, const_threads_shared = 512;
+    uint64_t plan_id = 0;
+    std::vector<double> h_const;  // [forward unpadded | transposed unpadded]
+    ~TTPlan() override;
 };
 
 // Shared-memory carve-up (doubles), identical on host and device:
@@ -95,6 +106,10 @@ int tt_launch_general(const TTPlan *pl, const TTFdProgram &prog, const double *d
                       double *d_out, cudaStream_t st);
 int tt_launch_shared(const TTPlan *pl, const TTSharedProgram &prog, const double *d_points,
                      int64_t N, double *d_out, cudaStream_t st);
+void ttc_forget(const TTPlan *pl);
+int ttc_launch_value(const TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st);
+int ttc_launch_shared(const TTPlan *pl, const TTSharedProgram &prog, const double *d_points,
+                      int64_t N, double *d_out, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
@@ -326,7 +341,7 @@ static int tt_launch_kernel(K kernel, const TTPlan *pl, const TTCfg &cfg, int64_
 // cores the generic one.  X(QPT, LC, MAXT)
 // (a launch with `threads` picks the first entry whose MAXT >= threads: keep MAXT ascending)
 #define TT_RESIDENT_CONFIGS(X) \
-    X(2, 8, 256) X(2, 12, 256) X(2, 16, 256) X(3, 12, 256) X(4, 12, 256) \
+    X(2, 8, 256) X(2, 12, 256) X(2, 16, 256) X(3, 12, 256) X(4, 12, 256) X(3, 12, 384) \
     X(1, 8, 512) X(1, 12, 512) X(1, 16, 512) X(2, 8, 512) X(2, 12, 512) X(2, 16, 512)
 #define TT_GENERIC_CONFIGS(X) X(2, 16, 256) X(1, 16, 512) X(2, 16, 512)
 #define TT_SHARED_RESIDENT_CONFIGS(X) \

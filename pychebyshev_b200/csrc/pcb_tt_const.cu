@@ -1,0 +1,383 @@
+// TT kernels whose coefficient cores live in the 64 KB __constant__ bank and reach the FP64 pipe
+// through the UNIFORM DATAPATH: `LDCU.64 URx, c[0x3][URy + imm]` loads a warp-uniform core element
+// into a uniform register and `DFMA Rd, Ra, URx, Rd` consumes it directly -- no shared-memory
+// wavefront, no LSU slot, no vector register for the operand.
+//
+// Why: the broadcast-LDS kernels (pcb_tt_chain/shared.cu) are co-limited by the shared-memory
+// pipe -- a broadcast LDS.128 costs 2 wavefronts, so with two query slots per thread the inner
+// loop needs 12 wavefronts per 24 DFMA, 92 % of the shared-memory bandwidth at full FP64 rate
+// (ncu: 60-72 % FP64 pipe).  The same loop fed from the constant bank measures 93 % of the FP64
+// peak (tools/probes/ldcu_probe*.cu; flat up to a 63 KB table).
+//
+// Two things ptxas needs before it emits LDCU instead of a per-lane LDC:
+//   * the core element is indexed as c_tt[int], never through a pointer that crossed a call;
+//   * NO loop around the chain whose induction depends on blockIdx (a persistent tile loop makes
+//     it drop the uniformity proof) -> these kernels run one tile per CTA.  Nothing is staged per
+//     CTA, so that costs nothing.
+//
+// The bank holds the unpadded forward cores G_k[i][j][l] and, for the finite-difference kernel,
+// the transposed cores G_k^T[l][j][i] of ONE plan per device at a time; `ttc_make_resident`
+// uploads on a plan switch, ordered against kernels of the previous plan on other streams.
+// Trains that do not fit (8192 doubles, ranks <= 16) use the shared-memory kernels.
+#include <mutex>
+
+#include "pcb_tt.cuh"
+
+namespace pcb {
+
+__constant__ double c_tt[TT_CONST_MAX];
+
+// ---- one step of a sweep: chunk of W output columns, rows (i, j) contiguous with stride W --------
+//   acc[l] = sum_{i,j} v[i] T_j(s) c_tt[base + (i n + j) W + l]
+template <int W, int QPT>
+__device__ __forceinline__ void ttc_chunk(int base, int r_in, int n, const double *v_in, int vstride,
+                                          const double (&s)[QPT], double *v_out) {
+    double acc[QPT][W], twos[QPT];
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+        twos[qq] = 2.0 * s[qq];
+#pragma unroll
+        for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
+    }
+    int gp = base;
+    for (int i = 0; i < r_in; ++i) {
+        double c0[QPT], c1[QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            const double vi = v_in[(i * QPT + qq) * vstride];
+            c0[qq] = vi;          // v[i] * T_0
+            c1[qq] = vi * s[qq];  // v[i] * T_1
+        }
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+#pragma unroll
+            for (int l = 0; l < W; ++l) {
+                const double gv = c_tt[gp + l];  // LDCU.64
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) acc[qq][l] = fma(c0[qq], gv, acc[qq][l]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                const double c2 = fma(twos[qq], c1[qq], -c0[qq]);  // T_{j+2} = 2 s T_{j+1} - T_j
+                c0[qq] = c1[qq];
+                c1[qq] = c2;
+            }
+            gp += W;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < W; ++l)
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) v_out[(l * QPT + qq) * vstride] = acc[qq][l];
+}
+
+// ---- coefficient pass: y_j = sum_{rows i} vrow[i] (sum_l c_tt[...][l] vacc[l]), j descending, with
+//      Clenshaw over the four stencil abscissae: b_j = y_j + 2 s b_{j+1} - b_{j+2} -----------------------
+template <int W, int QPT>
+__device__ __forceinline__ void ttc_coeff(int base, int r_rows, int n, const double *v_rows,
+                                          const double *v_acc, int vstride,
+                                          const double (&sm)[4][QPT], double (&f)[4][QPT]) {
+    // Clenshaw with the uniform recurrence b_j = y_j + 2 s b_{j+1} - b_{j+2} for j = n-1 .. 0 and
+    // f = b_0 - s b_1; only tw = 2 s is kept live (s = tw / 2 exactly).
+    double b1[4][QPT], b2[4][QPT], tw[4][QPT];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            b1[m][qq] = b2[m][qq] = 0.0;
+            tw[m][qq] = 2.0 * sm[m][qq];
+        }
+    for (int j = n - 1; j >= 0; --j) {
+        double acc[QPT][W];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+            for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
+        int gp = base + j * W;
+        for (int i = 0; i < r_rows; ++i) {
+            double li[QPT];
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) li[qq] = v_rows[(i * QPT + qq) * vstride];
+#pragma unroll
+            for (int l = 0; l < W; ++l) {
+                const double gv = c_tt[gp + l];
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) acc[qq][l] = fma(li[qq], gv, acc[qq][l]);
+            }
+            gp += n * W;
+        }
+        double y[QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) y[qq] = 0.0;
+#pragma unroll
+        for (int l = 0; l < W; ++l)
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq)
+                y[qq] = fma(acc[qq][l], v_acc[(l * QPT + qq) * vstride], y[qq]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                const double bn = fma(tw[m][qq], b1[m][qq], y[qq] - b2[m][qq]);
+                b2[m][qq] = b1[m][qq];
+                b1[m][qq] = bn;
+            }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) f[m][qq] = fma(-0.5 * tw[m][qq], b2[m][qq], b1[m][qq]);
+}
+
+#define TTC_CASE(FN, WW, ...)                             \
+    case WW:                                              \
+        if constexpr (WW <= RMAX) FN<WW, QPT>(__VA_ARGS__); \
+        break;
+#define TTC_SWITCH(FN, ...)                                                                       \
+    switch (w) {                                                                                  \
+        TTC_CASE(FN, 1, __VA_ARGS__) TTC_CASE(FN, 2, __VA_ARGS__) TTC_CASE(FN, 3, __VA_ARGS__)    \
+        TTC_CASE(FN, 4, __VA_ARGS__) TTC_CASE(FN, 5, __VA_ARGS__) TTC_CASE(FN, 6, __VA_ARGS__)    \
+        TTC_CASE(FN, 7, __VA_ARGS__) TTC_CASE(FN, 8, __VA_ARGS__) TTC_CASE(FN, 9, __VA_ARGS__)    \
+        TTC_CASE(FN, 10, __VA_ARGS__) TTC_CASE(FN, 11, __VA_ARGS__) TTC_CASE(FN, 12, __VA_ARGS__) \
+        TTC_CASE(FN, 13, __VA_ARGS__) TTC_CASE(FN, 14, __VA_ARGS__) TTC_CASE(FN, 15, __VA_ARGS__) \
+        TTC_CASE(FN, 16, __VA_ARGS__)                                                             \
+    }
+
+// v_out = step(v_in); ranks <= 16 means a single chunk, so v_out may alias v_in
+template <int QPT, int RMAX>
+__device__ __forceinline__ void ttc_step(int base, int w, int r_in, int n, const double *v_in,
+                                         double *v_out, int vstride, const double (&s)[QPT]) {
+    TTC_SWITCH(ttc_chunk, base, r_in, n, v_in, vstride, s, v_out)
+}
+
+template <int QPT, int RMAX>
+__device__ __forceinline__ void ttc_coeff_pass(int base, int w, int r_rows, int n,
+                                               const double *v_rows, const double *v_acc,
+                                               int vstride, const double (&sm)[4][QPT],
+                                               double (&f)[4][QPT]) {
+    TTC_SWITCH(ttc_coeff, base, r_rows, n, v_rows, v_acc, vstride, sm, f)
+}
+
+// ---- values ------------------------------------------------------------------------------------------
+template <int QPT, int RMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+ttc_value_kernel(const __grid_constant__ TTParams P, const double *__restrict__ pts, int64_t N,
+                 double *__restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    const int vstride = blockDim.x;
+    const int64_t q0 = (int64_t)blockIdx.x * vstride * QPT;  // one tile per CTA
+    const double *xrow[QPT];
+    tt_query_rows<QPT>(pts, N, P.D, q0, N, xrow);
+    double *vbuf = smem + threadIdx.x;
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) vbuf[qq * vstride] = 1.0;
+    for (int k = 0; k < P.D; ++k) {
+        double s[QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq)
+            s[qq] = tt_scale(__ldg(xrow[qq] + P.perm[k]), P.lo[k], P.hi[k]);
+        ttc_step<QPT, RMAX>(P.coff[k], P.r[k + 1], P.r[k], P.n[k], vbuf, vbuf, vstride, s);
+    }
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+        const int64_t q = q0 + qq * (int64_t)vstride + threadIdx.x;
+        if (q < N) out[q] = vbuf[qq * vstride];
+    }
+}
+
+// ---- pcb_tt_eval_fd algo 2 (see pcb_tt_shared.cu for the algorithm) -----------------------------------
+template <int QPT, int RMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+ttc_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__ TTSharedProgram prog,
+                     const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int vstride = blockDim.x;
+    const int D = P.D, G = prog.G;
+    const int64_t q0 = (int64_t)blockIdx.x * vstride * QPT;  // one tile per CTA
+    const double *xrow[QPT];
+    tt_query_rows<QPT>(pts, N, D, q0, N, xrow);
+    double *vL = smem + tid;
+    double *vR = vL + P.rmaxp * QPT * vstride;
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) vL[qq * vstride] = 1.0;
+    int lpos = 0;  // vL holds the left product over storage dims [0, lpos)
+    for (int t = 0; t < prog.n_slots; ++t) {
+        const int a = prog.slot_dim[t];
+        double s[QPT];
+        // right sweep over the transposed cores: vR = M_{a+1} ... M_{D-1} . 1
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) vR[qq * vstride] = 1.0;
+        for (int k = D - 1; k > a; --k) {
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq)
+                s[qq] = tt_scale(__ldg(xrow[qq] + P.perm[k]), P.lo[k], P.hi[k]);
+            ttc_step<QPT, RMAX>(P.coffT[k], P.r[k], P.r[k + 1], P.n[k], vR, vR, vstride, s);
+        }
+        // left sweep continues up to a
+        for (int k = lpos; k < a; ++k) {
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq)
+                s[qq] = tt_scale(__ldg(xrow[qq] + P.perm[k]), P.lo[k], P.hi[k]);
+            ttc_step<QPT, RMAX>(P.coff[k], P.r[k + 1], P.r[k], P.n[k], vL, vL, vstride, s);
+        }
+        lpos = a;
+        // stencil abscissae (reference _fd_step / _nudge_point): 0 query, 1 centre c, 2 c+h, 3 c-h
+        const double lo = P.lo[a], hi = P.hi[a];
+        const double h = (hi - lo) * 1e-4;
+        double sm[4][QPT], f[4][QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            const double x = __ldg(xrow[qq] + P.perm[a]);
+            const double c = tt_nudge(x, lo, hi, h);
+            sm[0][qq] = tt_scale(x, lo, hi);
+            sm[1][qq] = tt_scale(c, lo, hi);
+            sm[2][qq] = tt_scale(c + h, lo, hi);
+            sm[3][qq] = tt_scale(c - h, lo, hi);
+        }
+        // coefficient pass over the layout whose register-accumulated index is the wider one
+        if (P.r[a + 1] >= P.r[a])
+            ttc_coeff_pass<QPT, RMAX>(P.coff[a], P.r[a + 1], P.r[a], P.n[a], vL, vR, vstride, sm, f);
+        else
+            ttc_coeff_pass<QPT, RMAX>(P.coffT[a], P.r[a], P.r[a + 1], P.n[a], vR, vL, vstride, sm, f);
+        for (int g = 0; g < G; ++g) {
+            const int rs = prog.row_slot[g];
+            if (!(rs == t || (rs < 0 && t == 0))) continue;
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                const double res = rs < 0 ? f[0][qq]
+                                          : tt_fd_reduce(prog.row_ord[g], f[2][qq], f[1][qq], f[3][qq], h);
+                const int64_t q = q0 + qq * (int64_t)vstride + tid;
+                if (q < N) out[q * G + g] = res;
+            }
+        }
+    }
+}
+
+// ---- host side: residency of one plan per device in the constant bank ---------------------------------
+namespace {
+constexpr int MAX_DEV = 64;
+constexpr int MAX_TRACKED = 16;
+struct Residency {
+    std::mutex m;
+    uint64_t plan_id = 0;  // plan whose cores are in c_tt
+    cudaEvent_t uploaded = nullptr;
+    cudaStream_t upload_stream = nullptr;
+    // streams that launched kernels of the resident plan, with an event after their last launch
+    cudaStream_t users[MAX_TRACKED];
+    cudaEvent_t used[MAX_TRACKED] = {};
+    int n_users = 0;
+};
+Residency g_res[MAX_DEV];
+}  // namespace
+
+// Make `pl` the resident plan of its device and order `st` after the upload.  Returns with the
+// residency mutex LOCKED; the caller launches on `st` and then calls ttc_mark_used (which unlocks).
+static int ttc_make_resident(const TTPlan *pl, cudaStream_t st, Residency **out) {
+    if (pl->dev < 0 || pl->dev >= MAX_DEV) return fail(PCB_EINVAL, "device %d out of range", pl->dev);
+    Residency &R = g_res[pl->dev];
+    *out = &R;
+    R.m.lock();
+    if (!R.uploaded && cudaEventCreateWithFlags(&R.uploaded, cudaEventDisableTiming) != cudaSuccess) {
+        R.m.unlock();
+        return fail(PCB_ECUDA, "cudaEventCreate failed");
+    }
+    if (R.plan_id != pl->plan_id) {
+        // kernels of the previous plan may still be reading the bank on other streams
+        for (int i = 0; i < R.n_users; ++i)
+            if (R.users[i] != st) cudaStreamWaitEvent(st, R.used[i], 0);
+        const cudaError_t e =
+            cudaMemcpyToSymbolAsync(c_tt, pl->h_const.data(), pl->h_const.size() * sizeof(double), 0,
+                                    cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            R.m.unlock();
+            return fail(PCB_ECUDA, "upload of TT cores to the constant bank failed: %s",
+                        cudaGetErrorString(e));
+        }
+        cudaEventRecord(R.uploaded, st);
+        R.upload_stream = st;
+        R.plan_id = pl->plan_id;
+        R.n_users = 0;
+    } else if (st != R.upload_stream) {
+        cudaStreamWaitEvent(st, R.uploaded, 0);
+    }
+    return PCB_OK;
+}
+
+static void ttc_mark_used(Residency *R, cudaStream_t st) {
+    int slot = -1;
+    for (int i = 0; i < R->n_users; ++i)
+        if (R->users[i] == st) slot = i;
+    if (slot < 0) {
+        if (R->n_users == MAX_TRACKED) {
+            cudaDeviceSynchronize();  // too many streams to track: device-wide fence instead
+            R->n_users = 0;
+        }
+        slot = R->n_users++;
+        R->users[slot] = st;
+    }
+    if (!R->used[slot]) cudaEventCreateWithFlags(&R->used[slot], cudaEventDisableTiming);
+    cudaEventRecord(R->used[slot], st);
+    R->m.unlock();
+}
+
+void ttc_forget(const TTPlan *pl) {
+    if (pl->dev < 0 || pl->dev >= MAX_DEV) return;
+    std::lock_guard<std::mutex> lock(g_res[pl->dev].m);
+    if (g_res[pl->dev].plan_id == pl->plan_id) g_res[pl->dev].plan_id = 0;
+}
+
+template <typename K, typename... Args>
+static int ttc_launch(K kernel, const TTPlan *pl, int qpt, int threads, int nbuf, int64_t N,
+                      cudaStream_t st, Args... args) {
+    const size_t smem = (size_t)nbuf * pl->P.rmaxp * qpt * threads * sizeof(double);
+    if (smem > (size_t)pl->smem_optin)
+        return fail(PCB_EUNSUPPORTED, "TT uniform-path kernel needs %zu B of shared memory", smem);
+    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tile = (int64_t)threads * qpt;
+    const int64_t ntiles = (N + tile - 1) / tile;
+    if (ntiles > 0x7fffffffLL)
+        return fail(PCB_EINVAL, "batch of %lld queries is too large for one launch", (long long)N);
+    Residency *R = nullptr;
+    if (int rc = ttc_make_resident(pl, st, &R)) return rc;
+    kernel<<<(int)ntiles, threads, smem, st>>>(args...);
+    const cudaError_t e = cudaGetLastError();
+    ttc_mark_used(R, st);
+    g_launches.fetch_add(1);
+    if (e != cudaSuccess) return fail(PCB_ECUDA, "TT kernel launch failed: %s", cudaGetErrorString(e));
+    return PCB_OK;
+}
+
+// rank class of the plan: 8, 12 or 16 (only chunk widths up to it are compiled in)
+static int ttc_rank_class(const TTPlan *pl) {
+    int rmax = 1;
+    for (int k = 0; k <= pl->P.D; ++k) rmax = pl->P.r[k] > rmax ? pl->P.r[k] : rmax;
+    return rmax <= 8 ? 8 : (rmax <= 12 ? 12 : 16);
+}
+
+#define TTC_VALUE(Q, R)                                                                           \
+    if (pl->const_qpt == Q && rc_ == R)                                                           \
+        return ttc_launch(ttc_value_kernel<Q, R, 512>, pl, Q, threads, 1, N, st, pl->P, d_points, N, \
+                          d_out);
+#define TTC_SHARED(Q, R, T)                                                                       \
+    if (pl->const_qpt == Q && rc_ == R && threads <= T)                                           \
+        return ttc_launch(ttc_fd_shared_kernel<Q, R, T>, pl, Q, threads, 2, N, st, pl->P, prog,     \
+                          d_points, N, d_out);
+
+int ttc_launch_value(const TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+    const int threads = pl->const_threads_value, rc_ = ttc_rank_class(pl);
+    TTC_VALUE(2, 8) TTC_VALUE(2, 12) TTC_VALUE(2, 16) TTC_VALUE(1, 8) TTC_VALUE(1, 12) TTC_VALUE(1, 16)
+    return fail(PCB_EUNSUPPORTED, "no uniform-path TT value kernel for this configuration");
+}
+
+int ttc_launch_shared(const TTPlan *pl, const TTSharedProgram &prog, const double *d_points,
+                      int64_t N, double *d_out, cudaStream_t st) {
+    const int threads = pl->const_threads_shared, rc_ = ttc_rank_class(pl);
+    TTC_SHARED(2, 8, 256) TTC_SHARED(2, 12, 256) TTC_SHARED(2, 16, 256)
+    TTC_SHARED(2, 8, 384) TTC_SHARED(2, 12, 384) TTC_SHARED(2, 16, 384)
+    TTC_SHARED(2, 8, 512) TTC_SHARED(2, 12, 512) TTC_SHARED(2, 16, 512)
+    TTC_SHARED(1, 8, 512) TTC_SHARED(1, 12, 512) TTC_SHARED(1, 16, 512)
+    return fail(PCB_EUNSUPPORTED, "no uniform-path TT shared-FD kernel for this configuration");
+}
+
+}  // namespace pcb

@@ -49,7 +49,7 @@ print(json.dumps(res))
 
 
 def main():
-    configs = [(0, 0), (2, 256), (2, 384), (2, 512), (1, 512), (1, 256), (3, 256), (4, 256)]
+    configs = [tuple(int(v) for v in c.split('x')) for c in os.environ.get('TT_CONFIGS', '0x0,2x256,2x384,2x512,1x512,3x256,3x384,4x256').split(',')]
     for q, t in configs:
         env = dict(os.environ)
         if q:
