@@ -51,7 +51,8 @@ struct FullPlan : PlanBase {
     int G = 0;
     double *d_nodes = nullptr;    // nodes then weights, dims concatenated
     double *d_weights = nullptr;
-    double *d_tensors = nullptr;  // G C-order tensors
+    double *d_tensors = nullptr;  // G tensors interleaved in blocks of GB outputs: [block][elem][GB]
+    int GB = 1;
     double *d_prepared = nullptr; // G prepared (fragment-ordered, zero-padded) tensors
     bool dmma_ok = false;
     DmmaParams dm;
@@ -67,6 +68,7 @@ struct FullPlan : PlanBase {
 // FMA evaluator
 // ---------------------------------------------------------------------------------------------
 
+template <int GB, int DM>
 __global__ void __launch_bounds__(FULL_FMA_THREADS)
 full_fma_kernel(const __grid_constant__ GridDesc gd, int G, const double *__restrict__ nodes,
                 const double *__restrict__ weights, const double *__restrict__ tensors,
@@ -76,14 +78,11 @@ full_fma_kernel(const __grid_constant__ GridDesc gd, int G, const double *__rest
     const int stride = blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N;
          q += (int64_t)gridDim.x * blockDim.x) {
-        int off = 0;
-        for (int d = 0; d < gd.D; ++d) {
-            grid_weight_row(__ldg(pts + q * gd.D + d), gd.n[d], nodes + gd.node_off + off,
-                            weights + gd.node_off + off, ws + (size_t)off * stride, stride);
-            off += gd.n[d];
-        }
-        for (int g = 0; g < G; ++g)
-            out[q * G + g] = grid_contract(gd, tensors + gd.tensor_off + g * gd.size, ws, stride);
+        const double *x = pts + q * gd.D;
+        double wl[GRID_NL];
+        const bool regs = grid_weights(gd, nodes, weights, [&](int d) { return __ldg(x + d); }, ws,
+                                       stride, wl);
+        grid_eval_outputs<GB, DM>(gd, tensors, G, ws, stride, wl, regs, out + q * G, 1);
     }
 }
 
@@ -128,9 +127,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 // D(8x8) += A(8x4) * B(4x8), fp64 tensor core (SASS: DMMA.8x8x4)
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+    // not volatile: a pure function of its operands, so the scheduler may interleave the
+    // independent accumulator chains and the weighted folds freely
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
 }
 
 struct DmmaSmem {
@@ -474,18 +475,23 @@ extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, co
     }
     DeviceGuard guard(dev);
     const size_t nb = (size_t)gd.sum_n * sizeof(double);
-    const size_t tb = (size_t)gd.size * sizeof(double);
+    pl->GB = grid_pick_gb(G);
+    const int nblk = (G + pl->GB - 1) / pl->GB;
+    const size_t tcount = (size_t)gd.size * nblk * pl->GB;
     if (!guard.ok || cudaMalloc(&pl->d_nodes, 2 * nb) != cudaSuccess ||
-        cudaMalloc(&pl->d_tensors, tb * G) != cudaSuccess) {
+        cudaMalloc(&pl->d_tensors, tcount * sizeof(double)) != cudaSuccess) {
         delete pl;
         return fail(PCB_ENOMEM, "device allocation for the full-tensor plan failed");
     }
     pl->d_weights = pl->d_nodes + gd.sum_n;
     bool ok = cudaMemcpy(pl->d_nodes, nodes_cat, nb, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(pl->d_weights, weights_cat, nb, cudaMemcpyHostToDevice) == cudaSuccess;
-    for (int g = 0; ok && g < G; ++g)
-        ok = cudaMemcpy(pl->d_tensors + (size_t)g * gd.size, tensors_host[g], tb,
-                        cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) {
+        std::vector<double> il(tcount);
+        grid_interleave(tensors_host, G, pl->GB, gd.size, il.data());
+        ok = cudaMemcpy(pl->d_tensors, il.data(), tcount * sizeof(double), cudaMemcpyHostToDevice) ==
+             cudaSuccess;
+    }
     if (!ok) {
         delete pl;
         return fail(PCB_ECUDA, "upload of the full-tensor plan failed");
@@ -561,14 +567,17 @@ extern "C" PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory",
                     pl->gd.sum_n);
-    PCB_CUDA(cudaFuncSetAttribute(full_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const void *kernel = GRID_KERNEL_TABLE(full_fma_kernel, pl->GB, grid_pick_dm(pl->gd.D));
+    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, full_fma_kernel, FULL_FMA_THREADS, smem));
+    PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FULL_FMA_THREADS, smem));
     const int64_t want = (N + FULL_FMA_THREADS - 1) / FULL_FMA_THREADS;
     const int64_t cap = (int64_t)pl->sm_count * (per_sm > 0 ? per_sm : 1);
     const int grid = (int)(want < cap ? want : cap);
-    full_fma_kernel<<<grid, FULL_FMA_THREADS, smem, st>>>(pl->gd, pl->G, pl->d_nodes, pl->d_weights,
-                                                         pl->d_tensors, d_points, N, d_out);
+    int G = pl->G;
+    void *args[] = {(void *)&pl->gd, (void *)&G, (void *)&pl->d_nodes, (void *)&pl->d_weights,
+                    (void *)&pl->d_tensors, (void *)&d_points, (void *)&N, (void *)&d_out};
+    PCB_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(FULL_FMA_THREADS), args, smem, st));
     g_launches.fetch_add(1);
     PCB_CUDA(cudaGetLastError());
     return PCB_OK;

@@ -13,7 +13,7 @@ namespace pcb {
 constexpr int PW_THREADS = 128;
 
 struct SplinePlan : PlanBase {
-    int D = 0, P = 0, G = 0;
+    int D = 0, P = 0, G = 0, GB = 1;
     int max_sum_n = 0;
     int *d_num_knots = nullptr;  // [D] then knot_off [D]
     int *d_knot_off = nullptr;
@@ -21,7 +21,7 @@ struct SplinePlan : PlanBase {
     GridDesc *d_desc = nullptr;  // [P]
     double *d_nodes = nullptr;   // all pieces: nodes then weights (same offsets)
     double *d_weights = nullptr;
-    double *d_tensors = nullptr;
+    double *d_tensors = nullptr;  // per piece: [block][elem][GB]
     ~SplinePlan() override {
         if (d_num_knots) cudaFree(d_num_knots);
         if (d_knots) cudaFree(d_knots);
@@ -32,21 +32,18 @@ struct SplinePlan : PlanBase {
 };
 
 struct SliderPlan : PlanBase {
-    int D = 0, S = 0, G = 0;
-    int max_sum_n = 0;
+    int D = 0, S = 0, G = 0, GB = 1;
+    int max_sum_n = 0, max_D = 1;
     double pivot = 0.0;
-    GridDesc *d_desc = nullptr;      // [S]; tensor_off unused (see d_tensor_off)
-    int *d_group_off = nullptr;      // [S+1] then group dims, then out_slide [G]
-    int *d_group_dims = nullptr;
-    int *d_out_slide = nullptr;
-    long long *d_tensor_off = nullptr;  // [G][S], -1 when unused
+    GridDesc *d_desc = nullptr;  // [S]
+    int *d_ints = nullptr;       // group_off [S+1] | group dims | out_slide [G] | row_out [G] | slide_G [S]
+    int *d_group_dims = nullptr, *d_out_slide = nullptr, *d_row_out = nullptr, *d_slide_G = nullptr;
     double *d_nodes = nullptr;
     double *d_weights = nullptr;
-    double *d_tensors = nullptr;
+    double *d_tensors = nullptr;  // per slide: its outputs interleaved [block][elem][GB]
     ~SliderPlan() override {
         if (d_desc) cudaFree(d_desc);
-        if (d_group_off) cudaFree(d_group_off);
-        if (d_tensor_off) cudaFree(d_tensor_off);
+        if (d_ints) cudaFree(d_ints);
         if (d_nodes) cudaFree(d_nodes);
         if (d_tensors) cudaFree(d_tensors);
     }
@@ -61,6 +58,7 @@ spline_lookup_kernel(int D, const int *__restrict__ num_knots, const int *__rest
         piece[q] = spline_piece_index(D, num_knots, knot_off, knots, pts + q * D);
 }
 
+template <int GB, int DM>
 __global__ void __launch_bounds__(PW_THREADS)
 spline_eval_kernel(int D, int G, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
                    const double *__restrict__ knots, const GridDesc *__restrict__ desc,
@@ -76,54 +74,56 @@ spline_eval_kernel(int D, int G, const int *__restrict__ num_knots, const int *_
         const int p = spline_piece_index(D, num_knots, knot_off, knots, x);
         if (piece_out) piece_out[q] = p;
         const GridDesc gd = desc[p];
-        int off = 0;
-        for (int d = 0; d < D; ++d) {
-            grid_weight_row(__ldg(x + d), gd.n[d], nodes + gd.node_off + off,
-                            weights + gd.node_off + off, ws + (size_t)off * stride, stride);
-            off += gd.n[d];
-        }
-        for (int g = 0; g < G; ++g)
-            out[q * G + g] = grid_contract(gd, tensors + gd.tensor_off + g * gd.size, ws, stride);
+        double wl[GRID_NL];
+        const bool regs = grid_weights(gd, nodes, weights, [&](int d) { return __ldg(x + d); }, ws,
+                                       stride, wl);
+        grid_eval_outputs<GB, DM>(gd, tensors, G, ws, stride, wl, regs, out + q * G, 1);
     }
 }
 
+// Row g of the slider reads output `row_out[g]` of slide `out_slide[g]`; value rows
+// (out_slide = -1) accumulate output 0 of every slide; cross-slide rows (-2) are exactly 0.
+template <int GB, int DM>
 __global__ void __launch_bounds__(PW_THREADS)
 slider_eval_kernel(int D, int S, int G, double pivot, const GridDesc *__restrict__ desc,
                    const int *__restrict__ group_off, const int *__restrict__ group_dims,
-                   const int *__restrict__ out_slide, const long long *__restrict__ tensor_off,
-                   const double *__restrict__ nodes, const double *__restrict__ weights,
-                   const double *__restrict__ tensors, const double *__restrict__ pts, int64_t N,
-                   double *__restrict__ out) {
+                   const int *__restrict__ out_slide, const int *__restrict__ row_out,
+                   const int *__restrict__ slide_G, const double *__restrict__ nodes,
+                   const double *__restrict__ weights, const double *__restrict__ tensors,
+                   const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
     extern __shared__ __align__(16) double smem[];
     double *ws = smem + threadIdx.x;
     const int stride = blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N;
          q += (int64_t)gridDim.x * blockDim.x) {
         const double *x = pts + q * D;
-        for (int g = 0; g < G; ++g) {
-            const int os = out_slide[g];
-            double result;
-            if (os == -2) {
-                result = 0.0;  // cross-slide mixed partial, slider.py:297-298
-            } else {
-                // value row: pivot + sum_s (slide_s - pivot), left to right (slider.py:310-318);
-                // derivative row: the owning slide only (slider.py:301-307)
-                result = os == -1 ? pivot : 0.0;
-                const int s_lo = os == -1 ? 0 : os, s_hi = os == -1 ? S : os + 1;
-                for (int s = s_lo; s < s_hi; ++s) {
-                    const GridDesc gd = desc[s];
-                    const int *dims = group_dims + group_off[s];
-                    int off = 0;
-                    for (int d = 0; d < gd.D; ++d) {
-                        grid_weight_row(__ldg(x + dims[d]), gd.n[d], nodes + gd.node_off + off,
-                                        weights + gd.node_off + off, ws + (size_t)off * stride, stride);
-                        off += gd.n[d];
+        double *o = out + q * G;
+        // value rows start from the pivot (slider.py:310), cross-slide rows are exactly 0 (:297)
+        for (int g = 0; g < G; ++g) o[g] = out_slide[g] == -1 ? pivot : 0.0;
+        for (int s = 0; s < S; ++s) {
+            const int sg = slide_G[s];
+            if (sg == 0) continue;
+            const GridDesc gd = desc[s];
+            const int *dims = group_dims + group_off[s];
+            double wl[GRID_NL];
+            const bool regs = grid_weights(gd, nodes, weights,
+                                           [&](int d) { return __ldg(x + dims[d]); }, ws, stride, wl);
+            for (int b = 0; b * GB < sg; ++b) {
+                double r[GB];
+                grid_contract<GB, DM>(gd, tensors + gd.tensor_off + (long long)b * gd.size * GB, ws,
+                                  stride, wl, regs, r);
+#pragma unroll
+                for (int j = 0; j < GB; ++j) {
+                    const int so = b * GB + j;
+                    if (so >= sg) continue;
+                    for (int g = 0; g < G; ++g) {
+                        if (out_slide[g] == s && row_out[g] == so)
+                            o[g] = r[j];  // derivative row owned by this slide (:301-307)
+                        else if (out_slide[g] == -1 && so == 0 && row_out[g] == 0)
+                            o[g] = o[g] + (r[j] - pivot);  // left to right over the slides (:310-318)
                     }
-                    const double v = grid_contract(gd, tensors + tensor_off[(size_t)g * S + s], ws, stride);
-                    result = os == -1 ? result + (v - pivot) : v;
                 }
             }
-            out[q * G + g] = result;
         }
     }
 }
@@ -150,10 +150,11 @@ static int grid_launch_dims(const PlanBase *pl, const void *kernel, int threads,
 
 using namespace pcb;
 
-extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num_knots, const double *knots_cat,
-                                      int P, const int32_t *piece_n, const double *piece_nodes_cat,
-                                      const double *piece_weights_cat, int G,
-                                      const double *const *piece_tensors_host, void **plan) {
+extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num_knots,
+                                              const double *knots_cat, int P, const int32_t *piece_n,
+                                              const double *piece_nodes_cat,
+                                              const double *piece_weights_cat, int G,
+                                              const double *const *piece_tensors_host, void **plan) {
     PCB_REQUIRE(plan && num_knots && piece_n && piece_nodes_cat && piece_weights_cat &&
                     piece_tensors_host, "null argument");
     PCB_REQUIRE(D >= 1 && D <= GRID_MAXD, "num_dimensions %d outside [1, %d]", D, GRID_MAXD);
@@ -177,11 +178,13 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
     pl->D = D;
     pl->P = P;
     pl->G = G;
+    pl->GB = grid_pick_gb(G);
     int cc = 0;
     if (int rc = device_props(dev, &pl->sm_count, &pl->smem_optin, &cc)) {
         delete pl;
         return rc;
     }
+    const int nblk = (G + pl->GB - 1) / pl->GB;
     std::vector<GridDesc> desc(P);
     long long node_total = 0, tensor_total = 0;
     for (int p = 0; p < P; ++p) {
@@ -202,25 +205,24 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
             gd.size *= nn;
         }
         node_total += gd.sum_n;
-        tensor_total += gd.size * G;
+        tensor_total += gd.size * nblk * pl->GB;
         if (gd.sum_n > pl->max_sum_n) pl->max_sum_n = gd.sum_n;
     }
+    std::vector<double> il((size_t)tensor_total);
+    for (int p = 0; p < P; ++p)
+        grid_interleave(piece_tensors_host + (size_t)p * G, G, pl->GB, desc[p].size,
+                        il.data() + desc[p].tensor_off);
     DeviceGuard guard(dev);
     bool ok = guard.ok && upload(&pl->d_num_knots, meta.data(), meta.size()) &&
               upload(&pl->d_knots, knots_cat, (size_t)total_knots) &&
               upload(&pl->d_desc, desc.data(), desc.size()) &&
               upload<double>(&pl->d_nodes, nullptr, (size_t)(2 * node_total)) &&
-              upload<double>(&pl->d_tensors, nullptr, (size_t)tensor_total);
+              upload(&pl->d_tensors, il.data(), il.size());
     if (ok) {
         pl->d_knot_off = pl->d_num_knots + D;
         pl->d_weights = pl->d_nodes + node_total;
         ok = cudaMemcpy(pl->d_nodes, piece_nodes_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
              cudaMemcpy(pl->d_weights, piece_weights_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess;
-        for (int p = 0; ok && p < P; ++p)
-            for (int g = 0; ok && g < G; ++g)
-                ok = cudaMemcpy(pl->d_tensors + desc[p].tensor_off + g * desc[p].size,
-                                piece_tensors_host[(size_t)p * G + g], desc[p].size * 8,
-                                cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) {
         delete pl;
@@ -230,8 +232,8 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
     return PCB_OK;
 }
 
-extern "C" PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int64_t N, int32_t *d_piece,
-                                 void *stream) {
+extern "C" PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int64_t N,
+                                         int32_t *d_piece, void *stream) {
     SplinePlan *pl = static_cast<SplinePlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_SPLINE, "not a spline plan");
     PCB_REQUIRE(N >= 0, "negative N");
@@ -248,7 +250,7 @@ extern "C" PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int
 }
 
 extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64_t N, double *d_out,
-                               int32_t *d_piece, void *stream) {
+                                       int32_t *d_piece, void *stream) {
     SplinePlan *pl = static_cast<SplinePlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_SPLINE, "not a spline plan");
     PCB_REQUIRE(N >= 0, "negative N");
@@ -258,21 +260,26 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    const void *kernel = GRID_KERNEL_TABLE(spline_eval_kernel, pl->GB, grid_pick_dm(pl->D));
     int grid = 0;
-    if (int rc = grid_launch_dims(pl, (const void *)spline_eval_kernel, PW_THREADS, smem, N, &grid)) return rc;
-    spline_eval_kernel<<<grid, PW_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-        pl->D, pl->G, pl->d_num_knots, pl->d_knot_off, pl->d_knots, pl->d_desc, pl->d_nodes,
-        pl->d_weights, pl->d_tensors, d_points, N, d_out, d_piece);
+    if (int rc = grid_launch_dims(pl, kernel, PW_THREADS, smem, N, &grid)) return rc;
+    void *args[] = {(void *)&pl->D, (void *)&pl->G, (void *)&pl->d_num_knots, (void *)&pl->d_knot_off,
+                    (void *)&pl->d_knots, (void *)&pl->d_desc, (void *)&pl->d_nodes,
+                    (void *)&pl->d_weights, (void *)&pl->d_tensors, (void *)&d_points, (void *)&N,
+                    (void *)&d_out, (void *)&d_piece};
+    PCB_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(PW_THREADS), args, smem,
+                              static_cast<cudaStream_t>(stream)));
     g_launches.fetch_add(1);
     PCB_CUDA(cudaGetLastError());
     return PCB_OK;
 }
 
 extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32_t *group_size,
-                                      const int32_t *group_dims_cat, const int32_t *slide_n_cat,
-                                      const double *slide_nodes_cat, const double *slide_weights_cat,
-                                      double pivot_value, int G, const int32_t *out_slide,
-                                      const double *const *slide_tensors_host, void **plan) {
+                                              const int32_t *group_dims_cat, const int32_t *slide_n_cat,
+                                              const double *slide_nodes_cat,
+                                              const double *slide_weights_cat, double pivot_value, int G,
+                                              const int32_t *out_slide,
+                                              const double *const *slide_tensors_host, void **plan) {
     PCB_REQUIRE(plan && group_size && group_dims_cat && slide_n_cat && slide_nodes_cat &&
                     slide_weights_cat && out_slide && slide_tensors_host, "null argument");
     PCB_REQUIRE(D >= 1 && D <= 4096 && S >= 1 && S <= D, "invalid slider shape D=%d S=%d", D, S);
@@ -290,8 +297,7 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
         return rc;
     }
     std::vector<GridDesc> desc(S);
-    std::vector<int> ints;  // group_off [S+1] | group dims | out_slide [G]
-    ints.resize(S + 1);
+    std::vector<int> group_off(S + 1);
     int gpos = 0;
     long long node_total = 0;
     for (int s = 0; s < S; ++s) {
@@ -303,9 +309,10 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
             return fail(PCB_EUNSUPPORTED, "slide %d has %d dims (supported: 1..%d)", s, gs, GRID_MAXD);
         }
         gd.D = gs;
+        if (gs > pl->max_D) pl->max_D = gs;
         gd.size = 1;
         gd.node_off = (int)node_total;
-        ints[s] = gpos;
+        group_off[s] = gpos;
         for (int d = 0; d < gs; ++d) {
             const int dim = group_dims_cat[gpos + d];
             const int nn = slide_n_cat[gpos + d];
@@ -321,46 +328,75 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
         node_total += gd.sum_n;
         if (gd.sum_n > pl->max_sum_n) pl->max_sum_n = gd.sum_n;
     }
-    ints[S] = gpos;
-    for (int i = 0; i < gpos; ++i) ints.push_back(group_dims_cat[i]);
+    group_off[S] = gpos;
+    // per-slide output lists: output 0 = value tensor (when a value row exists), then one output
+    // per derivative row owned by the slide
+    std::vector<std::vector<const double *>> outs(S);
+    std::vector<int> row_out(G, 0);
+    int first_value_row = -1;
     for (int g = 0; g < G; ++g) {
         if (out_slide[g] < -2 || out_slide[g] >= S) {
             delete pl;
             return fail(PCB_EINVAL, "out_slide[%d]=%d invalid", g, out_slide[g]);
         }
-        ints.push_back(out_slide[g]);
+        if (out_slide[g] == -1 && first_value_row < 0) first_value_row = g;
     }
-    // tensors actually referenced
-    std::vector<long long> toff((size_t)G * S, -1);
-    long long tensor_total = 0;
-    for (int g = 0; g < G; ++g)
-        for (int s = 0; s < S; ++s)
-            if (out_slide[g] == -1 || out_slide[g] == s) {
+    for (int s = 0; s < S; ++s)
+        outs[s].push_back(first_value_row >= 0 ? slide_tensors_host[(size_t)first_value_row * S + s]
+                                               : nullptr);
+    for (int g = 0; g < G; ++g) {
+        const int os = out_slide[g];
+        if (os == -1) {
+            for (int s = 0; s < S; ++s)
                 if (!slide_tensors_host[(size_t)g * S + s]) {
                     delete pl;
                     return fail(PCB_EINVAL, "missing tensor for row %d slide %d", g, s);
                 }
-                toff[(size_t)g * S + s] = tensor_total;
-                tensor_total += desc[s].size;
+        } else if (os >= 0) {
+            if (!slide_tensors_host[(size_t)g * S + os]) {
+                delete pl;
+                return fail(PCB_EINVAL, "missing tensor for row %d slide %d", g, os);
             }
+            row_out[g] = (int)outs[os].size();
+            outs[os].push_back(slide_tensors_host[(size_t)g * S + os]);
+        }
+    }
+    std::vector<int> slide_G(S);
+    int maxg = 1;
+    for (int s = 0; s < S; ++s) {
+        // a slide with only the (absent) value slot and no derivative rows has nothing to do
+        slide_G[s] = (outs[s].size() == 1 && !outs[s][0]) ? 0 : (int)outs[s].size();
+        if (slide_G[s] > maxg) maxg = slide_G[s];
+    }
+    pl->GB = grid_pick_gb(maxg);
+    long long tensor_total = 0;
+    for (int s = 0; s < S; ++s) {
+        desc[s].tensor_off = tensor_total;
+        tensor_total += desc[s].size * ((slide_G[s] + pl->GB - 1) / pl->GB) * pl->GB;
+    }
+    std::vector<double> il((size_t)(tensor_total > 0 ? tensor_total : 1));
+    for (int s = 0; s < S; ++s)
+        if (slide_G[s] > 0)
+            grid_interleave(outs[s].data(), slide_G[s], pl->GB, desc[s].size,
+                            il.data() + desc[s].tensor_off);
+    std::vector<int> ints(group_off);
+    for (int i = 0; i < gpos; ++i) ints.push_back(group_dims_cat[i]);
+    for (int g = 0; g < G; ++g) ints.push_back(out_slide[g]);
+    for (int g = 0; g < G; ++g) ints.push_back(row_out[g]);
+    for (int s = 0; s < S; ++s) ints.push_back(slide_G[s]);
     DeviceGuard guard(dev);
     bool ok = guard.ok && upload(&pl->d_desc, desc.data(), desc.size()) &&
-              upload(&pl->d_group_off, ints.data(), ints.size()) &&
-              upload(&pl->d_tensor_off, toff.data(), toff.size()) &&
+              upload(&pl->d_ints, ints.data(), ints.size()) &&
               upload<double>(&pl->d_nodes, nullptr, (size_t)(2 * node_total)) &&
-              upload<double>(&pl->d_tensors, nullptr, (size_t)tensor_total);
+              upload(&pl->d_tensors, il.data(), il.size());
     if (ok) {
-        pl->d_group_dims = pl->d_group_off + S + 1;
+        pl->d_group_dims = pl->d_ints + S + 1;
         pl->d_out_slide = pl->d_group_dims + gpos;
+        pl->d_row_out = pl->d_out_slide + G;
+        pl->d_slide_G = pl->d_row_out + G;
         pl->d_weights = pl->d_nodes + node_total;
         ok = cudaMemcpy(pl->d_nodes, slide_nodes_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
              cudaMemcpy(pl->d_weights, slide_weights_cat, node_total * 8, cudaMemcpyHostToDevice) == cudaSuccess;
-        for (int g = 0; ok && g < G; ++g)
-            for (int s = 0; ok && s < S; ++s)
-                if (toff[(size_t)g * S + s] >= 0)
-                    ok = cudaMemcpy(pl->d_tensors + toff[(size_t)g * S + s],
-                                    slide_tensors_host[(size_t)g * S + s], desc[s].size * 8,
-                                    cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) {
         delete pl;
@@ -370,7 +406,8 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
     return PCB_OK;
 }
 
-extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream) {
+extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, double *d_out,
+                                       void *stream) {
     SliderPlan *pl = static_cast<SliderPlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_SLIDER, "not a slider plan");
     PCB_REQUIRE(N >= 0, "negative N");
@@ -380,11 +417,16 @@ extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    const void *kernel = GRID_KERNEL_TABLE(slider_eval_kernel, pl->GB, grid_pick_dm(pl->max_D));
     int grid = 0;
-    if (int rc = grid_launch_dims(pl, (const void *)slider_eval_kernel, PW_THREADS, smem, N, &grid)) return rc;
-    slider_eval_kernel<<<grid, PW_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-        pl->D, pl->S, pl->G, pl->pivot, pl->d_desc, pl->d_group_off, pl->d_group_dims, pl->d_out_slide,
-        pl->d_tensor_off, pl->d_nodes, pl->d_weights, pl->d_tensors, d_points, N, d_out);
+    if (int rc = grid_launch_dims(pl, kernel, PW_THREADS, smem, N, &grid)) return rc;
+    void *args[] = {(void *)&pl->D, (void *)&pl->S, (void *)&pl->G, (void *)&pl->pivot,
+                    (void *)&pl->d_desc, (void *)&pl->d_ints, (void *)&pl->d_group_dims,
+                    (void *)&pl->d_out_slide, (void *)&pl->d_row_out, (void *)&pl->d_slide_G,
+                    (void *)&pl->d_nodes, (void *)&pl->d_weights, (void *)&pl->d_tensors,
+                    (void *)&d_points, (void *)&N, (void *)&d_out};
+    PCB_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(PW_THREADS), args, smem,
+                              static_cast<cudaStream_t>(stream)));
     g_launches.fetch_add(1);
     PCB_CUDA(cudaGetLastError());
     return PCB_OK;
