@@ -151,6 +151,17 @@ PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32_t *group_s
 PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Native .pcb loader (no Python on the path): the C++ twin of the reference's stand-alone readers
+ * (examples/binary_reader/reader.c, readers/rust/src/lib.rs, readers/julia/src/PCBReader.jl).
+ * Parses the v1 layout of _binary.py:157-421, rebuilds nodes/weights the way the reference does on
+ * load, and creates a VALUE plan (one output per point).  *kind: 1 approximation, 2 spline.
+ * ------------------------------------------------------------------------------------------ */
+PCB_API int pcb_plan_from_file(int dev, const char *path, void **plan, int *kind, int *D);
+
+/* Values of any plan kind (the plan's own number of outputs per point). */
+PCB_API int pcb_plan_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Roofline probes (bench.py): measured FP64 pipe peaks of the device, in TFLOP/s.
  *   kind 0 = DFMA (register-resident FMA chains), 1 = DMMA (mma.sync m8n8k4 f64),
  *   kind 2 = both interleaved in every warp (sum of the two flop counts)

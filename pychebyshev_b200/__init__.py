@@ -19,6 +19,14 @@ from .tt import ChebyshevTT
 __version__ = "0.1.0"
 
 
+def load_plan(path, device=None):
+    """Native ``.pcb`` -> device value plan (``plan.eval(points)`` -> (N, 1)); see
+    ``pcb_plan_from_file`` in ``include/pcb_b200.h``."""
+    from ._engine import FilePlan
+
+    return FilePlan(path, device)
+
+
 @dataclass(frozen=True)
 class Domain:
     """Typed wrapper for per-dimension ``(lo, hi)`` bounds (reference ``__init__.py:35-45``)."""
@@ -59,5 +67,6 @@ __all__ = [
     "Domain",
     "Ns",
     "SpecialPoints",
+    "load_plan",
     "__version__",
 ]

@@ -389,6 +389,25 @@ class SliderPlan(DevicePlan):
         _lib.check(_lib.load().pcb_slider_eval(self._handle, d_points, n, d_out, stream))
 
 
+class FilePlan(DevicePlan):
+    """A value plan built natively from a ``.pcb`` file (``pcb_plan_from_file``): no Python
+    object, no NumPy grid arithmetic -- the C++ twin of the reference's stand-alone readers."""
+
+    def __init__(self, path, device=None):
+        import os
+
+        lib = _lib.load()
+        dev = require_device(device)
+        handle, kind, ndim = C.c_void_p(), C.c_int32(), C.c_int32()
+        _lib.check(lib.pcb_plan_from_file(dev, os.fsencode(os.fspath(path)), C.byref(handle),
+                                          C.byref(kind), C.byref(ndim)))
+        super().__init__(handle, dev, int(ndim.value), 1)
+        self.kind = {1: "approx", 2: "spline"}[int(kind.value)]
+
+    def _launch(self, d_points, n, d_out, stream):
+        _lib.check(_lib.load().pcb_plan_eval(self._handle, d_points, n, d_out, stream))
+
+
 def probe_fp64_peak(kind: int, device=None):
     """Measured FP64 peak (TFLOP/s) of the DFMA (0) or DMMA (1) pipe on this device."""
     lib = _lib.load()

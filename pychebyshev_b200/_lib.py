@@ -50,6 +50,8 @@ SIGNATURES = {
     "pcb_slider_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _f64p, _f64p,
                                          C.c_double, C.c_int, _i32p, C.POINTER(_f64p), _vpp]),
     "pcb_slider_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pcb_plan_from_file": (C.c_int, [C.c_int, C.c_char_p, _vpp, _i32p, _i32p]),
+    "pcb_plan_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pcb_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "pcb_launch_count": (C.c_int64, []),
 }

@@ -347,3 +347,31 @@ def test_tt_large_batch_properties():
     fd = tt.eval_multi_batch(pts[:1_000_000], g["fd_orders"][:4], algo=1)
     assert torch.isfinite(fd).all()
     scale_close(fd[:, 0].cpu().numpy(), full[:1_000_000].cpu().numpy(), "fd value row", rel=1e-13)
+
+
+# ------------------------------------------------------------------------------------------
+# native .pcb loader (no Python grid arithmetic on the path)
+# ------------------------------------------------------------------------------------------
+
+def test_native_pcb_loader_matches_reference(tmp_path):
+    """pcb_plan_from_file on the reference's own fixture files (bytes stored in the goldens)
+    against the values the reference computed after loading them."""
+    import pychebyshev_b200 as pcb
+
+    gold = G.load("pcb_files")
+    for key, kind, ndim in (("approx_2d_simple", "approx", 2), ("spline_1d_kink", "spline", 1)):
+        path = tmp_path / f"{key}.pcb"
+        path.write_bytes(gold[key + "_bytes"].tobytes())
+        plan = pcb.load_plan(path)
+        assert plan.kind == kind and plan.ndim == ndim
+        got = plan.eval(gold[key + "_points"])[:, 0]
+        scale_close(got, gold[key + "_values"], f"native loader {key}")
+    # a file written by this package (5D), read back natively vs through the Python class
+    g = G.load("full_4d")
+    n = [int(v) for v in g["n_nodes"]]
+    cheb = pcb.ChebyshevApproximation.from_values(g["tensor"], 4, g["domain"].tolist(), n)
+    path = tmp_path / "full4d.pcb"
+    cheb.save(path)
+    native = pcb.load_plan(path).eval(g["points"])[:, 0]
+    scale_close(native, g["values"][:, 0], "native loader full_4d",
+                factor=G.extrapolation_factor(cheb.domain, cheb.nodes, cheb.weights, g["points"]))

@@ -116,3 +116,59 @@ def test_class_tag_mismatch_and_save_guards(tmp_path):
     cheb.save(q, format="pickle")
     back = pcb.ChebyshevApproximation.load(q)
     assert np.array_equal(back.tensor_values, cheb.tensor_values) and back.function is None
+
+
+def test_native_loader_rejects_corrupt_files_before_touching_cuda(tmp_path):
+    """pcb_plan_from_file validates like _binary.py (no GPU needed: parsing comes first)."""
+    import ctypes as C
+
+    from pychebyshev_b200 import _lib
+
+    lib = _lib.load()
+    good = pcbfile.approx_bytes([[0.0, 1.0]], [2], np.array([1.0, 2.0]))
+    cases = {
+        "bad magic": b"XXXX" + good[4:],
+        "unsupported .pcb major version": good[:4] + b"\x02" + good[5:],
+        "reserved": good[:8] + b"\x01\x00\x00\x00" + good[12:],
+        "unexpected EOF": good[:-3],
+        "unknown class_tag": good[:6] + struct.pack("<H", 9) + good[8:],
+        "must be <": pcbfile.approx_bytes([[1.0, 1.0]], [2], np.array([1.0, 2.0])),
+    }
+    for needle, raw in cases.items():
+        path = tmp_path / "bad.pcb"
+        path.write_bytes(raw)
+        plan, kind, ndim = C.c_void_p(), C.c_int32(), C.c_int32()
+        rc = lib.pcb_plan_from_file(0, str(path).encode(), C.byref(plan), C.byref(kind), C.byref(ndim))
+        assert rc == _lib.PCB_EINVAL, needle
+        assert needle in _lib.last_error(), (needle, _lib.last_error())
+    rc = lib.pcb_plan_from_file(0, b"/nonexistent/file.pcb", C.byref(plan), None, None)
+    assert rc == _lib.PCB_EINVAL and "cannot open" in _lib.last_error()
+
+
+def test_files_written_here_are_readable_by_the_reference_c_reader(tmp_path):
+    """oracle/_ref/pcb_reader is the reference's examples/binary_reader/reader.c compiled as is
+    (oracle/ref_reader.mk).  It must parse our files and reproduce the interpolant's values."""
+    import os
+    import subprocess
+
+    from oracle import np_oracle as O
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "pcb_reader")
+    if not os.path.exists(exe):
+        if not os.path.exists("/root/reference/examples/binary_reader/reader.c"):
+            pytest.skip("reference C reader not built and reference tree absent")
+        subprocess.run(["make", "-C", os.path.join(root, "oracle"), "-f", "ref_reader.mk"], check=True,
+                       capture_output=True)
+    g = G.load("full_3d")
+    n, nodes, weights, dms = G.full_parts(g)
+    cheb = pcb.ChebyshevApproximation.from_values(g["tensor"], 3, g["domain"].tolist(), n)
+    path = tmp_path / "full3d.pcb"
+    cheb.save(path)
+    pts = g["points"][:12]
+    ref = O.full_eval_batch(g["tensor"], nodes, weights, dms, pts, [0, 0, 0])
+    for p, want in zip(pts, ref):
+        out = subprocess.run([exe, str(path)] + [repr(float(v)) for v in p], capture_output=True,
+                             text=True, check=True).stdout
+        got = float(out.strip().split()[-1])
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (got, want)
