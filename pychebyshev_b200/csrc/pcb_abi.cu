@@ -1,10 +1,15 @@
 // C-ABI plumbing shared by all plans + the FP64 roofline probes.
-#include "pcb_common.cuh"
+#include "pcb_cbank.cuh"
 
 namespace pcb {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+
+uint64_t next_plan_id() {
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
+}
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];

@@ -6,6 +6,9 @@
 //   The reference groups points by piece and calls the piece evaluator per group; on the device
 //   every query simply indexes its piece's descriptor, so no bucketing pass is needed.
 // Slider: replaces a loop of ChebyshevSlider.eval (reference slider.py:247-318).
+#include <cstdlib>
+
+#include "pcb_cbank.cuh"
 #include "pcb_grid.cuh"
 
 namespace pcb {
@@ -22,7 +25,13 @@ struct SplinePlan : PlanBase {
     double *d_nodes = nullptr;   // all pieces: nodes then weights (same offsets)
     double *d_weights = nullptr;
     double *d_tensors = nullptr;  // per piece: [block][elem][GB]
-    ~SplinePlan() override {
+    // uniform-datapath path: all piece tensors + descriptors in this module's constant bank
+    bool bank_ok = false;
+    uint64_t plan_id = 0;
+    std::vector<double> h_bank;
+    std::vector<GridDesc> h_desc;
+    ~SplinePlan() override;
+    void free_all() {
         if (d_num_knots) cudaFree(d_num_knots);
         if (d_knots) cudaFree(d_knots);
         if (d_desc) cudaFree(d_desc);
@@ -41,7 +50,12 @@ struct SliderPlan : PlanBase {
     double *d_nodes = nullptr;
     double *d_weights = nullptr;
     double *d_tensors = nullptr;  // per slide: its outputs interleaved [block][elem][GB]
-    ~SliderPlan() override {
+    bool bank_ok = false;
+    uint64_t plan_id = 0;
+    std::vector<double> h_bank;
+    std::vector<GridDesc> h_desc;
+    ~SliderPlan() override;
+    void free_all() {
         if (d_desc) cudaFree(d_desc);
         if (d_ints) cudaFree(d_ints);
         if (d_nodes) cudaFree(d_nodes);
@@ -128,6 +142,198 @@ slider_eval_kernel(int D, int S, int G, double pivot, const GridDesc *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Uniform-datapath variants (small plans): every piece / slide tensor lives in this module's
+// constant bank and is read with warp-uniform `LDCU` feeding `DFMA ... UR` directly, so the tensor
+// costs no LSU slot and no vector register.  Control flow is kept warp-uniform: the spline kernel
+// loops over the pieces PRESENT in the warp (vote) and every lane contracts that piece's tensor
+// with its own weights; the lanes that belong to the piece keep the result (select, no branch).
+// One query per thread and no grid-stride loop (ptxas needs that to prove uniformity).
+// ---------------------------------------------------------------------------------------------
+constexpr int BANK_DOUBLES = 7680;  // 60 KB of tensors + 64 descriptors of 72 B in the 64 KB bank
+constexpr int BANK_GRIDS = 32;  // also the width of the spline kernel's piece-presence mask
+__constant__ double c_grid[BANK_DOUBLES];
+__constant__ GridDesc c_gdesc[BANK_GRIDS];
+static ConstBank g_grid_bank;
+
+template <int LEVEL, int D, int GB>
+struct GridContractU {
+    __device__ __forceinline__ static void run(int base, const GridDesc &gd, const int (&stride)[GRID_MAXD],
+                                               const double *ws, int wstride,
+                                               const double (&wl)[GRID_NL], double (&out)[GB]) {
+        const int nl = gd.n[LEVEL];
+        if constexpr (LEVEL == D - 1) {
+            double part[4][GB];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int j = 0; j < GB; ++j) part[c][j] = 0.0;
+#pragma unroll
+            for (int i = 0; i < GRID_NL; ++i) {
+                if (i < nl) {
+#pragma unroll
+                    for (int j = 0; j < GB; ++j)
+                        part[i & 3][j] = fma(wl[i], c_grid[base + i * GB + j], part[i & 3][j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < GB; ++j) out[j] = (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < GB; ++j) out[j] = 0.0;
+            const int st = stride[LEVEL] * GB;
+            const double *wnext = ws + (size_t)nl * wstride;
+            for (int i = 0; i < nl; ++i) {
+                double sub[GB];
+                GridContractU<(LEVEL + 1 < D ? LEVEL + 1 : LEVEL), D, GB>::run(base + i * st, gd, stride,
+                                                                              wnext, wstride, wl, sub);
+                const double w = ws[i * wstride];
+#pragma unroll
+                for (int j = 0; j < GB; ++j) out[j] = fma(w, sub[j], out[j]);
+            }
+        }
+    }
+};
+
+#define GRIDU_CASE(K)                                                                   \
+    case K:                                                                             \
+        if constexpr (K <= DM) GridContractU<0, K, GB>::run(base, gd, stride, ws, wstride, wl, out); \
+        break;
+
+// Contract output block `b` of bank-resident grid `gd` (a reference INTO c_gdesc: uniform).
+template <int GB, int DM>
+__device__ __forceinline__ void grid_contract_u(const GridDesc &gd, int b, const double *ws,
+                                                int wstride, const double (&wl)[GRID_NL],
+                                                double (&out)[GB]) {
+    int stride[GRID_MAXD];
+    int s = 1;
+    for (int d = gd.D - 1; d >= 0; --d) {
+        stride[d] = s;
+        s *= gd.n[d];
+    }
+    const int base = (int)gd.tensor_off + b * (int)gd.size * GB;
+#pragma unroll
+    for (int j = 0; j < GB; ++j) out[j] = 0.0;
+    switch (gd.D) {
+        GRIDU_CASE(1) GRIDU_CASE(2) GRIDU_CASE(3) GRIDU_CASE(4) GRIDU_CASE(5) GRIDU_CASE(6)
+        GRIDU_CASE(7) GRIDU_CASE(8)
+    }
+}
+
+template <int GB, int DM>
+__global__ void __launch_bounds__(PW_THREADS)
+spline_uniform_kernel(int D, int G, int P, const int *__restrict__ num_knots,
+                      const int *__restrict__ knot_off, const double *__restrict__ knots,
+                      const double *__restrict__ nodes, const double *__restrict__ weights,
+                      const double *__restrict__ pts, int64_t N, double *__restrict__ out,
+                      int32_t *__restrict__ piece_out) {
+    extern __shared__ __align__(16) double smem[];
+    double *ws = smem + threadIdx.x;
+    const int stride = blockDim.x;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double *x = pts + (q < N ? q : N - 1) * D;  // tail lanes recompute the last query
+    const int mine = spline_piece_index(D, num_knots, knot_off, knots, x);
+    if (piece_out && q < N) piece_out[q] = mine;
+    double wl[GRID_NL];
+    {
+        // The bank path requires every piece to have the same node counts (the reference's splines
+        // do: spline.py n_nodes is per dimension), so trip counts come from piece 0 -- uniform --
+        // and only the node / weight OFFSET is per lane.  Per-lane trip counts (or doing this under
+        // `if (mine == p)`) make ptxas abandon the uniform datapath for the whole kernel.
+        const long long shift = c_gdesc[mine].node_off - c_gdesc[0].node_off;
+        grid_weights(c_gdesc[0], nodes + shift, weights + shift, [&](int d) { return __ldg(x + d); }, ws,
+                     stride, wl);
+    }
+    // pieces present in this warp: REDUX leaves the mask in a uniform register, so the skip below
+    // is a uniform branch (P <= 32 on this path)
+    const unsigned present = __reduce_or_sync(0xffffffffu, 1u << mine);
+    for (int b = 0; b * GB < G; ++b) {
+        double r[GB];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) r[j] = 0.0;
+        for (int p = 0; p < P; ++p) {
+            if (!((present >> p) & 1u)) continue;
+            double sub[GB];
+            grid_contract_u<GB, DM>(c_gdesc[p], b, ws, stride, wl, sub);
+#pragma unroll
+            for (int j = 0; j < GB; ++j) r[j] = mine == p ? sub[j] : r[j];
+        }
+        if (q < N) {
+#pragma unroll
+            for (int j = 0; j < GB; ++j)
+                if (b * GB + j < G) out[q * G + b * GB + j] = r[j];
+        }
+    }
+}
+
+template <int GB, int DM>
+__global__ void __launch_bounds__(PW_THREADS)
+slider_uniform_kernel(int D, int S, int G, double pivot, const int *__restrict__ group_off,
+                      const int *__restrict__ group_dims, const int *__restrict__ out_slide,
+                      const int *__restrict__ row_out, const int *__restrict__ slide_G,
+                      const double *__restrict__ nodes, const double *__restrict__ weights,
+                      const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    double *ws = smem + threadIdx.x;
+    const int stride = blockDim.x;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t qc = q < N ? q : N - 1;
+    const double *x = pts + qc * D;
+    double *o = out + qc * G;  // tail lanes redo (and rewrite) the last query: same values
+    for (int g = 0; g < G; ++g) o[g] = out_slide[g] == -1 ? pivot : 0.0;
+    for (int s = 0; s < S; ++s) {
+        const int sg = slide_G[s];
+        if (sg == 0) continue;
+        const GridDesc &gd = c_gdesc[s];
+        const int *dims = group_dims + group_off[s];
+        double wl[GRID_NL];
+        grid_weights(gd, nodes, weights, [&](int d) { return __ldg(x + dims[d]); }, ws, stride, wl);
+        for (int b = 0; b * GB < sg; ++b) {
+            double r[GB];
+            grid_contract_u<GB, DM>(gd, b, ws, stride, wl, r);
+#pragma unroll
+            for (int j = 0; j < GB; ++j) {
+                const int so = b * GB + j;
+                if (so >= sg) continue;
+                for (int g = 0; g < G; ++g) {
+                    if (out_slide[g] == s && row_out[g] == so)
+                        o[g] = r[j];
+                    else if (out_slide[g] == -1 && so == 0 && row_out[g] == 0)
+                        o[g] = o[g] + (r[j] - pivot);
+                }
+            }
+        }
+    }
+}
+
+// Can these grids live in the bank?  (tensors incl. all output blocks, descriptors, n_last)
+static bool bank_fits(const std::vector<GridDesc> &desc, long long tensor_total) {
+    if (tensor_total > BANK_DOUBLES || desc.size() > (size_t)BANK_GRIDS) return false;
+    for (const GridDesc &gd : desc)
+        if (gd.n[gd.D - 1] > GRID_NL) return false;
+    return true;
+}
+
+static bool same_shape(const std::vector<GridDesc> &desc) {
+    for (const GridDesc &gd : desc) {
+        if (gd.D != desc[0].D) return false;
+        for (int d = 0; d < gd.D; ++d)
+            if (gd.n[d] != desc[0].n[d]) return false;
+    }
+    return true;
+}
+
+static int bank_acquire(int dev, uint64_t plan_id, const std::vector<double> &h_bank,
+                        const std::vector<GridDesc> &h_desc, cudaStream_t st) {
+    return g_grid_bank.acquire(dev, plan_id, st, [&](cudaStream_t s) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_grid, h_bank.data(), h_bank.size() * sizeof(double), 0,
+                                                cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyToSymbolAsync(c_gdesc, h_desc.data(), h_desc.size() * sizeof(GridDesc), 0,
+                                       cudaMemcpyHostToDevice, s);
+    });
+}
+
 template <typename T>
 static bool upload(T **dptr, const T *src, size_t count) {
     if (count == 0) count = 1;
@@ -144,6 +350,15 @@ static int grid_launch_dims(const PlanBase *pl, const void *kernel, int threads,
     const int64_t cap = (int64_t)pl->sm_count * (per_sm > 0 ? per_sm : 1);
     *grid = (int)(want < cap ? want : cap);
     return PCB_OK;
+}
+
+SplinePlan::~SplinePlan() {
+    g_grid_bank.forget(dev, plan_id);
+    free_all();
+}
+SliderPlan::~SliderPlan() {
+    g_grid_bank.forget(dev, plan_id);
+    free_all();
 }
 
 }  // namespace pcb
@@ -212,6 +427,12 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
     for (int p = 0; p < P; ++p)
         grid_interleave(piece_tensors_host + (size_t)p * G, G, pl->GB, desc[p].size,
                         il.data() + desc[p].tensor_off);
+    pl->plan_id = next_plan_id();
+    pl->bank_ok = bank_fits(desc, tensor_total) && same_shape(desc) && !getenv("PCB_NO_BANK");
+    if (pl->bank_ok) {
+        pl->h_bank = il;
+        pl->h_desc = desc;
+    }
     DeviceGuard guard(dev);
     bool ok = guard.ok && upload(&pl->d_num_knots, meta.data(), meta.size()) &&
               upload(&pl->d_knots, knots_cat, (size_t)total_knots) &&
@@ -260,6 +481,24 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    if (pl->bank_ok) {
+        const void *uk = GRID_KERNEL_TABLE(spline_uniform_kernel, pl->GB, grid_pick_dm(pl->D));
+        PCB_CUDA(cudaFuncSetAttribute(uk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t blocks = (N + PW_THREADS - 1) / PW_THREADS;
+        PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (int rc = bank_acquire(pl->dev, pl->plan_id, pl->h_bank, pl->h_desc, st)) return rc;
+        void *uargs[] = {(void *)&pl->D, (void *)&pl->G, (void *)&pl->P, (void *)&pl->d_num_knots,
+                         (void *)&pl->d_knot_off, (void *)&pl->d_knots, (void *)&pl->d_nodes,
+                         (void *)&pl->d_weights, (void *)&d_points, (void *)&N, (void *)&d_out,
+                         (void *)&d_piece};
+        const cudaError_t e = cudaLaunchKernel(uk, dim3((unsigned)blocks), dim3(PW_THREADS), uargs, smem, st);
+        g_grid_bank.release(pl->dev, st);
+        g_launches.fetch_add(1);
+        PCB_CUDA(e);
+        PCB_CUDA(cudaGetLastError());
+        return PCB_OK;
+    }
     const void *kernel = GRID_KERNEL_TABLE(spline_eval_kernel, pl->GB, grid_pick_dm(pl->D));
     int grid = 0;
     if (int rc = grid_launch_dims(pl, kernel, PW_THREADS, smem, N, &grid)) return rc;
@@ -379,6 +618,12 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
         if (slide_G[s] > 0)
             grid_interleave(outs[s].data(), slide_G[s], pl->GB, desc[s].size,
                             il.data() + desc[s].tensor_off);
+    pl->plan_id = next_plan_id();
+    pl->bank_ok = bank_fits(desc, tensor_total) && !getenv("PCB_NO_BANK");
+    if (pl->bank_ok) {
+        pl->h_bank = il;
+        pl->h_desc = desc;
+    }
     std::vector<int> ints(group_off);
     for (int i = 0; i < gpos; ++i) ints.push_back(group_dims_cat[i]);
     for (int g = 0; g < G; ++g) ints.push_back(out_slide[g]);
@@ -417,6 +662,24 @@ extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    if (pl->bank_ok) {
+        const void *uk = GRID_KERNEL_TABLE(slider_uniform_kernel, pl->GB, grid_pick_dm(pl->max_D));
+        PCB_CUDA(cudaFuncSetAttribute(uk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t blocks = (N + PW_THREADS - 1) / PW_THREADS;
+        PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (int rc = bank_acquire(pl->dev, pl->plan_id, pl->h_bank, pl->h_desc, st)) return rc;
+        void *uargs[] = {(void *)&pl->D, (void *)&pl->S, (void *)&pl->G, (void *)&pl->pivot,
+                         (void *)&pl->d_ints, (void *)&pl->d_group_dims, (void *)&pl->d_out_slide,
+                         (void *)&pl->d_row_out, (void *)&pl->d_slide_G, (void *)&pl->d_nodes,
+                         (void *)&pl->d_weights, (void *)&d_points, (void *)&N, (void *)&d_out};
+        const cudaError_t e = cudaLaunchKernel(uk, dim3((unsigned)blocks), dim3(PW_THREADS), uargs, smem, st);
+        g_grid_bank.release(pl->dev, st);
+        g_launches.fetch_add(1);
+        PCB_CUDA(e);
+        PCB_CUDA(cudaGetLastError());
+        return PCB_OK;
+    }
     const void *kernel = GRID_KERNEL_TABLE(slider_eval_kernel, pl->GB, grid_pick_dm(pl->max_D));
     int grid = 0;
     if (int rc = grid_launch_dims(pl, kernel, PW_THREADS, smem, N, &grid)) return rc;

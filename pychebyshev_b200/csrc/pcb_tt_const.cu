@@ -19,8 +19,7 @@
 // the transposed cores G_k^T[l][j][i] of ONE plan per device at a time; `ttc_make_resident`
 // uploads on a plan switch, ordered against kernels of the previous plan on other streams.
 // Trains that do not fit (8192 doubles, ranks <= 16) use the shared-memory kernels.
-#include <mutex>
-
+#include "pcb_cbank.cuh"
 #include "pcb_tt.cuh"
 
 namespace pcb {
@@ -254,78 +253,10 @@ ttc_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__
     }
 }
 
-// ---- host side: residency of one plan per device in the constant bank ---------------------------------
-namespace {
-constexpr int MAX_DEV = 64;
-constexpr int MAX_TRACKED = 16;
-struct Residency {
-    std::mutex m;
-    uint64_t plan_id = 0;  // plan whose cores are in c_tt
-    cudaEvent_t uploaded = nullptr;
-    cudaStream_t upload_stream = nullptr;
-    // streams that launched kernels of the resident plan, with an event after their last launch
-    cudaStream_t users[MAX_TRACKED];
-    cudaEvent_t used[MAX_TRACKED] = {};
-    int n_users = 0;
-};
-Residency g_res[MAX_DEV];
-}  // namespace
+// ---- host side ----------------------------------------------------------------------------------------
+static ConstBank g_bank;  // residency of one plan per device in c_tt (pcb_cbank.cuh)
 
-// Make `pl` the resident plan of its device and order `st` after the upload.  Returns with the
-// residency mutex LOCKED; the caller launches on `st` and then calls ttc_mark_used (which unlocks).
-static int ttc_make_resident(const TTPlan *pl, cudaStream_t st, Residency **out) {
-    if (pl->dev < 0 || pl->dev >= MAX_DEV) return fail(PCB_EINVAL, "device %d out of range", pl->dev);
-    Residency &R = g_res[pl->dev];
-    *out = &R;
-    R.m.lock();
-    if (!R.uploaded && cudaEventCreateWithFlags(&R.uploaded, cudaEventDisableTiming) != cudaSuccess) {
-        R.m.unlock();
-        return fail(PCB_ECUDA, "cudaEventCreate failed");
-    }
-    if (R.plan_id != pl->plan_id) {
-        // kernels of the previous plan may still be reading the bank on other streams
-        for (int i = 0; i < R.n_users; ++i)
-            if (R.users[i] != st) cudaStreamWaitEvent(st, R.used[i], 0);
-        const cudaError_t e =
-            cudaMemcpyToSymbolAsync(c_tt, pl->h_const.data(), pl->h_const.size() * sizeof(double), 0,
-                                    cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) {
-            R.m.unlock();
-            return fail(PCB_ECUDA, "upload of TT cores to the constant bank failed: %s",
-                        cudaGetErrorString(e));
-        }
-        cudaEventRecord(R.uploaded, st);
-        R.upload_stream = st;
-        R.plan_id = pl->plan_id;
-        R.n_users = 0;
-    } else if (st != R.upload_stream) {
-        cudaStreamWaitEvent(st, R.uploaded, 0);
-    }
-    return PCB_OK;
-}
-
-static void ttc_mark_used(Residency *R, cudaStream_t st) {
-    int slot = -1;
-    for (int i = 0; i < R->n_users; ++i)
-        if (R->users[i] == st) slot = i;
-    if (slot < 0) {
-        if (R->n_users == MAX_TRACKED) {
-            cudaDeviceSynchronize();  // too many streams to track: device-wide fence instead
-            R->n_users = 0;
-        }
-        slot = R->n_users++;
-        R->users[slot] = st;
-    }
-    if (!R->used[slot]) cudaEventCreateWithFlags(&R->used[slot], cudaEventDisableTiming);
-    cudaEventRecord(R->used[slot], st);
-    R->m.unlock();
-}
-
-void ttc_forget(const TTPlan *pl) {
-    if (pl->dev < 0 || pl->dev >= MAX_DEV) return;
-    std::lock_guard<std::mutex> lock(g_res[pl->dev].m);
-    if (g_res[pl->dev].plan_id == pl->plan_id) g_res[pl->dev].plan_id = 0;
-}
+void ttc_forget(const TTPlan *pl) { g_bank.forget(pl->dev, pl->plan_id); }
 
 template <typename K, typename... Args>
 static int ttc_launch(K kernel, const TTPlan *pl, int qpt, int threads, int nbuf, int64_t N,
@@ -338,11 +269,14 @@ static int ttc_launch(K kernel, const TTPlan *pl, int qpt, int threads, int nbuf
     const int64_t ntiles = (N + tile - 1) / tile;
     if (ntiles > 0x7fffffffLL)
         return fail(PCB_EINVAL, "batch of %lld queries is too large for one launch", (long long)N);
-    Residency *R = nullptr;
-    if (int rc = ttc_make_resident(pl, st, &R)) return rc;
+    if (int rc = g_bank.acquire(pl->dev, pl->plan_id, st, [&](cudaStream_t s) {
+            return cudaMemcpyToSymbolAsync(c_tt, pl->h_const.data(), pl->h_const.size() * sizeof(double),
+                                           0, cudaMemcpyHostToDevice, s);
+        }))
+        return rc;
     kernel<<<(int)ntiles, threads, smem, st>>>(args...);
     const cudaError_t e = cudaGetLastError();
-    ttc_mark_used(R, st);
+    g_bank.release(pl->dev, st);
     g_launches.fetch_add(1);
     if (e != cudaSuccess) return fail(PCB_ECUDA, "TT kernel launch failed: %s", cudaGetErrorString(e));
     return PCB_OK;

@@ -1,6 +1,7 @@
 // ChebyshevTT: plan creation, launch-configuration choice and the C-ABI entry points.
 #include <cstdlib>
 
+#include "pcb_cbank.cuh"
 #include "pcb_tt.cuh"
 
 namespace pcb {
@@ -185,8 +186,7 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
     }
     // uniform-datapath path: unpadded forward (+ transposed) cores for the constant bank
     {
-        static std::atomic<uint64_t> next_id{1};
-        pl->plan_id = next_id.fetch_add(1);
+        pl->plan_id = next_plan_id();
         int fwd = 0, rmax = 1;
         for (int k = 0; k < D; ++k) {
             P.coff[k] = fwd;
