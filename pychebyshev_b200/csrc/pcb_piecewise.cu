@@ -6,6 +6,8 @@
 //   The reference groups points by piece and calls the piece evaluator per group; on the device
 //   every query simply indexes its piece's descriptor, so no bucketing pass is needed.
 // Slider: replaces a loop of ChebyshevSlider.eval (reference slider.py:247-318).
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "pcb_cbank.cuh"
@@ -14,6 +16,19 @@
 namespace pcb {
 
 constexpr int PW_THREADS = 128;
+
+// descriptor of a grid whose tensor / nodes / weights live in the constant bank (see below)
+struct BankGrid {
+    int D;
+    int n[GRID_MAXD];
+    int size;        // prod(n)
+    int tensor_off;  // bank index of output block 0
+    int node_off;    // bank index of the nodes (dims concatenated)
+    int weight_off;  // bank index of the weights
+    int scale_off;   // bank index of D prescale factors, then D scaled hit thresholds
+    int dims[GRID_MAXD];  // coordinate of the query each grid dimension reads
+    int outputs;          // tensors stored for this grid (slider: 0 = nothing to do)
+};
 
 struct SplinePlan : PlanBase {
     int D = 0, P = 0, G = 0, GB = 1;
@@ -29,7 +44,8 @@ struct SplinePlan : PlanBase {
     bool bank_ok = false;
     uint64_t plan_id = 0;
     std::vector<double> h_bank;
-    std::vector<GridDesc> h_desc;
+    std::vector<BankGrid> h_desc;
+    size_t bank_smem = 0;
     ~SplinePlan() override;
     void free_all() {
         if (d_num_knots) cudaFree(d_num_knots);
@@ -53,7 +69,8 @@ struct SliderPlan : PlanBase {
     bool bank_ok = false;
     uint64_t plan_id = 0;
     std::vector<double> h_bank;
-    std::vector<GridDesc> h_desc;
+    std::vector<BankGrid> h_desc;
+    size_t bank_smem = 0;
     ~SliderPlan() override;
     void free_all() {
         if (d_desc) cudaFree(d_desc);
@@ -143,50 +160,185 @@ slider_eval_kernel(int D, int S, int G, double pivot, const GridDesc *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// Uniform-datapath variants (small plans): every piece / slide tensor lives in this module's
-// constant bank and is read with warp-uniform `LDCU` feeding `DFMA ... UR` directly, so the tensor
-// costs no LSU slot and no vector register.  Control flow is kept warp-uniform: the spline kernel
-// loops over the pieces PRESENT in the warp (vote) and every lane contracts that piece's tensor
-// with its own weights; the lanes that belong to the piece keep the result (select, no branch).
-// One query per thread and no grid-stride loop (ptxas needs that to prove uniformity).
+// Uniform-datapath variants (small plans).  Tensors, nodes and barycentric weights of EVERY piece /
+// slide live in this module's constant bank and are read with warp-uniform `LDCU` feeding
+// `DFMA/DADD/DMUL ... UR` directly: the broadcast operands cost no LSU slot and no vector register.
+// A weight row is built in registers (unnormalised product form, 6 fp64 ops per node, no memory
+// traffic); its 1/sum is folded into the level-0 weights.  Control flow is kept warp-uniform:
+//   * one query per thread, no grid-stride loop (ptxas needs that to prove uniformity);
+//   * the spline kernel first counting-sorts the CTA's queries by piece (match + one shared atomic
+//     per piece per warp), so that all but <= P-1 warps of a CTA are single-piece; a warp then loops
+//     over the pieces PRESENT in it (REDUX -> uniform mask) and the lanes that belong to the piece
+//     store the result (predicated store, no branch around the math).
 // ---------------------------------------------------------------------------------------------
-constexpr int BANK_DOUBLES = 7680;  // 60 KB of tensors + 64 descriptors of 72 B in the 64 KB bank
-constexpr int BANK_GRIDS = 32;  // also the width of the spline kernel's piece-presence mask
+constexpr int BANK_THREADS = 256;
+constexpr int BANK_DOUBLES = 7808;  // 61 KB of tensors + nodes + weights (+ 2.75 KB descriptors)
+constexpr int BANK_GRIDS = 32;      // also the width of the spline kernel's piece-presence mask
 __constant__ double c_grid[BANK_DOUBLES];
-__constant__ GridDesc c_gdesc[BANK_GRIDS];
+__constant__ BankGrid c_bgrid[BANK_GRIDS];
 static ConstBank g_grid_bank;
 
+// 1/s without the fp64 division's slow-path CALL: a call inside the kernel's loops makes ptxas give
+// up on the uniform datapath for the whole kernel (every LDCU becomes a per-lane LDC).  s is a row
+// sum of moderate magnitude here (see the power-of-two prescale in bank_build), so the
+// flush-to-zero seed is safe; three Newton steps from the 20-bit seed leave <= 1 ulp.
+__device__ __forceinline__ double bank_rcp(double s) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+#pragma unroll
+    for (int it = 0; it < 3; ++it) y = fma(y, fma(-s, y, 1.0), y);
+    return y;
+}
+
+// Unnormalised barycentric row a[i] = w_i * prod_{k != i} (x - x_k), i < N, in registers; returns
+// sum_i a[i].  A node hit (|x - x_k| < 1e-14, first k) gives the one-hot row with sum 1
+// (barycentric.py:147-151).  x, the nodes (bank index nbase) and the hit threshold `eps_bits` are
+// in the grid dimension's PRESCALED units: bank_build multiplies them by one power of two per
+// dimension so that the node span is ~4 (every product of distances stays near 1 whatever the
+// domain width) -- exact, so each distance is the reference's times that power of two and the
+// normalised weights are bit-identical to the unscaled product form.  The weights are scaled by
+// another power of two (max |w| in [0.5, 1)), which the normalisation cancels.
+// N is a template argument (dispatched by a uniform switch) so that no per-node guard is needed:
+// ptxas if-converts such guards into per-lane predicates, which drags the bank reads off the
+// uniform path.
+template <int N, bool STORE>
+__device__ __forceinline__ double bank_row_n(double x, int nbase, int wbase, long long eps_bits,
+                                             double (&a)[GRID_NL], double *ws, int wstride, double fold) {
+    double d[N];
+    double pre = 1.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        d[i] = x - c_grid[nbase + i];
+        a[i] = pre;
+        pre *= d[i];
+    }
+    double suf = 1.0, sum = 0.0;
+    int hit = -1;
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        a[i] = c_grid[wbase + i] * a[i] * suf;
+        sum += a[i];
+        suf *= d[i];
+        // |d| < eps on the integer pipe (IEEE order of non-negative doubles = integer order; NaN
+        // compares false like the reference's fabs(d) < 1e-14); descending: the lowest index wins
+        if ((__double_as_longlong(d[i]) & 0x7fffffffffffffffLL) < eps_bits) hit = i;
+    }
+    if (hit >= 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = i == hit ? 1.0 : 0.0;
+        sum = 1.0;
+    }
+    if constexpr (STORE) {
+        // normalised row to the smem column; `fold` carries the last row's 1/sum into dim 0
+        const double inv = bank_rcp(sum);
+#pragma unroll
+        for (int i = 0; i < N; ++i) ws[i * wstride] = (a[i] * inv) * fold;
+    } else {
+#pragma unroll
+        for (int i = N; i < GRID_NL; ++i) a[i] = 0.0;
+    }
+    return sum;
+}
+
+#define BANK_ROW_CASE(K) \
+    case K: return bank_row_n<K, STORE>(x, nbase, wbase, eps_bits, a, ws, wstride, fold);
+
+// Row of an n-node dimension: STORE ? normalised (times `fold`) into the smem column ws :
+// unnormalised in a[] (entries >= n zero).  Returns the row sum.
+template <bool STORE>
+__device__ __forceinline__ double bank_row(double x, int n, int nbase, int wbase, long long eps_bits,
+                                           double (&a)[GRID_NL], double *ws, int wstride, double fold) {
+    static_assert(GRID_NL == 16, "the bank path dispatches 1..16 nodes");
+    switch (n) {
+        BANK_ROW_CASE(1) BANK_ROW_CASE(2) BANK_ROW_CASE(3) BANK_ROW_CASE(4) BANK_ROW_CASE(5)
+        BANK_ROW_CASE(6) BANK_ROW_CASE(7) BANK_ROW_CASE(8) BANK_ROW_CASE(9) BANK_ROW_CASE(10)
+        BANK_ROW_CASE(11) BANK_ROW_CASE(12) BANK_ROW_CASE(13) BANK_ROW_CASE(14) BANK_ROW_CASE(15)
+        BANK_ROW_CASE(16)
+    }
+    return 1.0;
+}
+
+// Weights of bank grid `g` at coordinates x(d): last dim unnormalised in wl[] (registers), dims
+// 0..D-2 normalised in the smem column ws; returns the factor still to be applied to the result
+// (1/sum of the last row for D = 1; folded into dim 0's row otherwise).
+template <typename Coord>
+__device__ __forceinline__ double bank_weights(const BankGrid &g, Coord x, double *ws, int wstride,
+                                               double (&wl)[GRID_NL]) {
+    const int D = g.D;
+    int off_last = 0;
+    for (int d = 0; d + 1 < D; ++d) off_last += g.n[d];
+    double fold = bank_rcp(bank_row<false>(x(D - 1) * c_grid[g.scale_off + D - 1], g.n[D - 1],
+                                           g.node_off + off_last, g.weight_off + off_last,
+                                           __double_as_longlong(c_grid[g.scale_off + D + D - 1]), wl,
+                                           nullptr, 0, 1.0));
+    int off = 0;
+    for (int d = 0; d + 1 < D; ++d) {
+        double a[GRID_NL];
+        bank_row<true>(x(d) * c_grid[g.scale_off + d], g.n[d], g.node_off + off, g.weight_off + off,
+                       __double_as_longlong(c_grid[g.scale_off + D + d]), a, ws + off * wstride, wstride,
+                       fold);
+        fold = 1.0;
+        off += g.n[d];
+    }
+    return fold;
+}
+
+// Innermost contraction: sum_i wl[i] * T[base + i*GB + j], i < N, four partial sums per output.
+// N is a template argument for the same reason as in bank_row_n (no per-element guards).
+template <int N, int GB>
+__device__ __forceinline__ void bank_dot_n(int base, const double (&wl)[GRID_NL], double (&out)[GB]) {
+    constexpr int C = N < 4 ? N : 4;
+    double part[C][GB];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const double t = c_grid[base + i * GB + j];
+            part[i % C][j] = i < C ? wl[i] * t : fma(wl[i], t, part[i % C][j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+        if constexpr (C == 4)
+            out[j] = (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
+        else if constexpr (C == 3)
+            out[j] = (part[0][j] + part[1][j]) + part[2][j];
+        else if constexpr (C == 2)
+            out[j] = part[0][j] + part[1][j];
+        else
+            out[j] = part[0][j];
+    }
+}
+
+#define BANK_DOT_CASE(K) \
+    case K: bank_dot_n<K, GB>(base, wl, out); break;
+
 template <int LEVEL, int D, int GB>
-struct GridContractU {
-    __device__ __forceinline__ static void run(int base, const GridDesc &gd, const int (&stride)[GRID_MAXD],
-                                               const double *ws, int wstride,
+struct BankContract {
+    __device__ __forceinline__ static void run(int base, const BankGrid &g, const double *ws, int wstride,
                                                const double (&wl)[GRID_NL], double (&out)[GB]) {
-        const int nl = gd.n[LEVEL];
+        const int nl = g.n[LEVEL];
         if constexpr (LEVEL == D - 1) {
-            double part[4][GB];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int j = 0; j < GB; ++j) part[c][j] = 0.0;
-#pragma unroll
-            for (int i = 0; i < GRID_NL; ++i) {
-                if (i < nl) {
-#pragma unroll
-                    for (int j = 0; j < GB; ++j)
-                        part[i & 3][j] = fma(wl[i], c_grid[base + i * GB + j], part[i & 3][j]);
-                }
+            switch (nl) {
+                BANK_DOT_CASE(1) BANK_DOT_CASE(2) BANK_DOT_CASE(3) BANK_DOT_CASE(4) BANK_DOT_CASE(5)
+                BANK_DOT_CASE(6) BANK_DOT_CASE(7) BANK_DOT_CASE(8) BANK_DOT_CASE(9) BANK_DOT_CASE(10)
+                BANK_DOT_CASE(11) BANK_DOT_CASE(12) BANK_DOT_CASE(13) BANK_DOT_CASE(14)
+                BANK_DOT_CASE(15) BANK_DOT_CASE(16)
             }
-#pragma unroll
-            for (int j = 0; j < GB; ++j) out[j] = (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
         } else {
 #pragma unroll
             for (int j = 0; j < GB; ++j) out[j] = 0.0;
-            const int st = stride[LEVEL] * GB;
+            // stride of this level from compile-time indices only: a dynamically indexed stride
+            // array is if-converted with per-lane predicates and drags every bank address (and
+            // with it every bank read) off the uniform datapath
+            int st = GB;
+#pragma unroll
+            for (int d = LEVEL + 1; d < D; ++d) st *= g.n[d];
             const double *wnext = ws + (size_t)nl * wstride;
             for (int i = 0; i < nl; ++i) {
                 double sub[GB];
-                GridContractU<(LEVEL + 1 < D ? LEVEL + 1 : LEVEL), D, GB>::run(base + i * st, gd, stride,
-                                                                              wnext, wstride, wl, sub);
+                BankContract<(LEVEL + 1 < D ? LEVEL + 1 : LEVEL), D, GB>::run(base + i * st, g, wnext,
+                                                                             wstride, wl, sub);
                 const double w = ws[i * wstride];
 #pragma unroll
                 for (int j = 0; j < GB; ++j) out[j] = fma(w, sub[j], out[j]);
@@ -195,143 +347,239 @@ struct GridContractU {
     }
 };
 
-#define GRIDU_CASE(K)                                                                   \
+#define BANK_CASE(K)                                                                    \
     case K:                                                                             \
-        if constexpr (K <= DM) GridContractU<0, K, GB>::run(base, gd, stride, ws, wstride, wl, out); \
+        if constexpr (K <= DM) BankContract<0, K, GB>::run(base, g, ws, wstride, wl, out); \
         break;
 
-// Contract output block `b` of bank-resident grid `gd` (a reference INTO c_gdesc: uniform).
+// Contract output block `b` of bank grid `g` (a reference INTO c_bgrid: uniform).
 template <int GB, int DM>
-__device__ __forceinline__ void grid_contract_u(const GridDesc &gd, int b, const double *ws,
-                                                int wstride, const double (&wl)[GRID_NL],
-                                                double (&out)[GB]) {
-    int stride[GRID_MAXD];
-    int s = 1;
-    for (int d = gd.D - 1; d >= 0; --d) {
-        stride[d] = s;
-        s *= gd.n[d];
-    }
-    const int base = (int)gd.tensor_off + b * (int)gd.size * GB;
+__device__ __forceinline__ void bank_contract(const BankGrid &g, int b, const double *ws, int wstride,
+                                              const double (&wl)[GRID_NL], double scale,
+                                              double (&out)[GB]) {
+    const int base = g.tensor_off + b * g.size * GB;
 #pragma unroll
     for (int j = 0; j < GB; ++j) out[j] = 0.0;
-    switch (gd.D) {
-        GRIDU_CASE(1) GRIDU_CASE(2) GRIDU_CASE(3) GRIDU_CASE(4) GRIDU_CASE(5) GRIDU_CASE(6)
-        GRIDU_CASE(7) GRIDU_CASE(8)
+    switch (g.D) {
+        BANK_CASE(1) BANK_CASE(2) BANK_CASE(3) BANK_CASE(4) BANK_CASE(5) BANK_CASE(6) BANK_CASE(7)
+        BANK_CASE(8)
+    }
+    if (g.D == 1) {
+#pragma unroll
+        for (int j = 0; j < GB; ++j) out[j] *= scale;
     }
 }
 
 template <int GB, int DM>
-__global__ void __launch_bounds__(PW_THREADS)
-spline_uniform_kernel(int D, int G, int P, const int *__restrict__ num_knots,
-                      const int *__restrict__ knot_off, const double *__restrict__ knots,
-                      const double *__restrict__ nodes, const double *__restrict__ weights,
-                      const double *__restrict__ pts, int64_t N, double *__restrict__ out,
-                      int32_t *__restrict__ piece_out) {
+__global__ void __launch_bounds__(BANK_THREADS)
+spline_bank_kernel(int D, int G, int P, const int *__restrict__ num_knots,
+                   const int *__restrict__ knot_off, const double *__restrict__ knots,
+                   const double *__restrict__ pts, int64_t N, double *__restrict__ out,
+                   int32_t *__restrict__ piece_out) {
     extern __shared__ __align__(16) double smem[];
-    double *ws = smem + threadIdx.x;
-    const int stride = blockDim.x;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const double *x = pts + (q < N ? q : N - 1) * D;  // tail lanes recompute the last query
-    const int mine = spline_piece_index(D, num_knots, knot_off, knots, x);
-    if (piece_out && q < N) piece_out[q] = mine;
-    double wl[GRID_NL];
+    __shared__ int s_cnt[BANK_GRIDS];
+    __shared__ unsigned short s_perm[BANK_THREADS];
+    __shared__ unsigned char s_piece[BANK_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t q0 = (int64_t)blockIdx.x * BANK_THREADS;
+    int mine;
     {
-        // The bank path requires every piece to have the same node counts (the reference's splines
-        // do: spline.py n_nodes is per dimension), so trip counts come from piece 0 -- uniform --
-        // and only the node / weight OFFSET is per lane.  Per-lane trip counts (or doing this under
-        // `if (mine == p)`) make ptxas abandon the uniform datapath for the whole kernel.
-        const long long shift = c_gdesc[mine].node_off - c_gdesc[0].node_off;
-        grid_weights(c_gdesc[0], nodes + shift, weights + shift, [&](int d) { return __ldg(x + d); }, ws,
-                     stride, wl);
+        // routing (spline.py:677-690) of the query this thread LOADS; tail lanes take the last one
+        const int64_t ql = q0 + tid < N ? q0 + tid : N - 1;
+        mine = spline_piece_index(D, num_knots, knot_off, knots, pts + ql * D);
+        if (piece_out && q0 + tid < N) piece_out[q0 + tid] = mine;
     }
-    // pieces present in this warp: REDUX leaves the mask in a uniform register, so the skip below
-    // is a uniform branch (P <= 32 on this path)
+    // counting sort of the CTA's queries by piece
+    if (tid < BANK_GRIDS) s_cnt[tid] = 0;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, mine);
+    const int leader = __ffs(peers) - 1;
+    int warp_off = 0;
+    if (lane == leader) warp_off = atomicAdd(&s_cnt[mine], __popc(peers));
+    warp_off = __shfl_sync(0xffffffffu, warp_off, leader);
+    __syncthreads();
+    int pos = warp_off + __popc(peers & ((1u << lane) - 1u));
+    for (int p = 0; p < P; ++p) pos += p < mine ? s_cnt[p] : 0;
+    s_perm[pos] = (unsigned short)tid;
+    s_piece[pos] = (unsigned char)mine;
+    __syncthreads();
+    // from here on this thread EVALUATES query s_perm[tid] of the CTA, which lies in piece `mine`
+    mine = s_piece[tid];
+    const int64_t q = q0 + s_perm[tid];
+    const bool live = q < N;
+    const double *x = pts + (live ? q : N - 1) * D;
+    double *o = out + (live ? q : N - 1) * G;
     const unsigned present = __reduce_or_sync(0xffffffffu, 1u << mine);
-    for (int b = 0; b * GB < G; ++b) {
-        double r[GB];
-#pragma unroll
-        for (int j = 0; j < GB; ++j) r[j] = 0.0;
-        for (int p = 0; p < P; ++p) {
-            if (!((present >> p) & 1u)) continue;
-            double sub[GB];
-            grid_contract_u<GB, DM>(c_gdesc[p], b, ws, stride, wl, sub);
-#pragma unroll
-            for (int j = 0; j < GB; ++j) r[j] = mine == p ? sub[j] : r[j];
-        }
-        if (q < N) {
+    for (int p = 0; p < P; ++p) {
+        if (!((present >> p) & 1u)) continue;  // uniform: REDUX leaves the mask in a uniform register
+        const BankGrid &g = c_bgrid[p];
+        const bool keep = live && mine == p;
+        double wl[GRID_NL];
+        const double inv = bank_weights(g, [&](int d) { return __ldg(x + d); }, smem + tid, BANK_THREADS, wl);
+        for (int b = 0; b * GB < G; ++b) {
+            double r[GB];
+            bank_contract<GB, DM>(g, b, smem + tid, BANK_THREADS, wl, inv, r);
 #pragma unroll
             for (int j = 0; j < GB; ++j)
-                if (b * GB + j < G) out[q * G + b * GB + j] = r[j];
+                if (keep && b * GB + j < G) o[b * GB + j] = r[j];
         }
     }
 }
 
+constexpr int SLIDER_ACC = 4;  // output rows accumulated in registers; further rows in global memory
+
 template <int GB, int DM>
-__global__ void __launch_bounds__(PW_THREADS)
-slider_uniform_kernel(int D, int S, int G, double pivot, const int *__restrict__ group_off,
-                      const int *__restrict__ group_dims, const int *__restrict__ out_slide,
-                      const int *__restrict__ row_out, const int *__restrict__ slide_G,
-                      const double *__restrict__ nodes, const double *__restrict__ weights,
-                      const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
+__global__ void __launch_bounds__(BANK_THREADS)
+slider_bank_kernel(int D, int S, int G, double pivot, const int *__restrict__ out_slide,
+                   const int *__restrict__ row_out, const double *__restrict__ pts, int64_t N,
+                   double *__restrict__ out) {
     extern __shared__ __align__(16) double smem[];
-    double *ws = smem + threadIdx.x;
-    const int stride = blockDim.x;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t qc = q < N ? q : N - 1;
+    const int64_t q = (int64_t)blockIdx.x * BANK_THREADS + threadIdx.x;
+    const bool live = q < N;
+    const int64_t qc = live ? q : N - 1;
     const double *x = pts + qc * D;
-    double *o = out + qc * G;  // tail lanes redo (and rewrite) the last query: same values
-    for (int g = 0; g < G; ++g) o[g] = out_slide[g] == -1 ? pivot : 0.0;
+    double *o = out + qc * G;
+    double acc[SLIDER_ACC];
+#pragma unroll
+    for (int g = 0; g < SLIDER_ACC; ++g) acc[g] = (g < G && out_slide[g] == -1) ? pivot : 0.0;
+    for (int g = SLIDER_ACC; g < G; ++g)
+        if (live) o[g] = out_slide[g] == -1 ? pivot : 0.0;
     for (int s = 0; s < S; ++s) {
-        const int sg = slide_G[s];
+        // every value that steers control flow comes from the constant bank: a branch on a GLOBAL
+        // load that follows per-lane global stores is not provably uniform for ptxas
+        const BankGrid &gr = c_bgrid[s];
+        const int sg = gr.outputs;
         if (sg == 0) continue;
-        const GridDesc &gd = c_gdesc[s];
-        const int *dims = group_dims + group_off[s];
         double wl[GRID_NL];
-        grid_weights(gd, nodes, weights, [&](int d) { return __ldg(x + dims[d]); }, ws, stride, wl);
+        double *ws = smem + threadIdx.x;
+        const double inv = bank_weights(gr, [&](int d) { return __ldg(x + gr.dims[d]); }, ws, BANK_THREADS, wl);
         for (int b = 0; b * GB < sg; ++b) {
             double r[GB];
-            grid_contract_u<GB, DM>(gd, b, ws, stride, wl, r);
+            bank_contract<GB, DM>(gr, b, ws, BANK_THREADS, wl, inv, r);
 #pragma unroll
             for (int j = 0; j < GB; ++j) {
                 const int so = b * GB + j;
                 if (so >= sg) continue;
-                for (int g = 0; g < G; ++g) {
-                    if (out_slide[g] == s && row_out[g] == so)
-                        o[g] = r[j];
-                    else if (out_slide[g] == -1 && so == 0 && row_out[g] == 0)
-                        o[g] = o[g] + (r[j] - pivot);
+                // row g takes output row_out[g] of slide out_slide[g]; value rows (-1) add
+                // (slide value - pivot) of every slide (slider.py:300-318)
+#pragma unroll
+                for (int g = 0; g < SLIDER_ACC; ++g) {
+                    if (g < G) {
+                        const int os = out_slide[g], ro = row_out[g];
+                        if (os == s && ro == so)
+                            acc[g] = r[j];
+                        else if (os == -1 && so == 0 && ro == 0)
+                            acc[g] = acc[g] + (r[j] - pivot);
+                    }
+                }
+                for (int g = SLIDER_ACC; g < G; ++g) {
+                    const int os = out_slide[g], ro = row_out[g];
+                    if (live) {
+                        if (os == s && ro == so)
+                            o[g] = r[j];
+                        else if (os == -1 && so == 0 && ro == 0)
+                            o[g] = o[g] + (r[j] - pivot);
+                    }
                 }
             }
         }
     }
+#pragma unroll
+    for (int g = 0; g < SLIDER_ACC; ++g)
+        if (live && g < G) o[g] = acc[g];
 }
 
-// Can these grids live in the bank?  (tensors incl. all output blocks, descriptors, n_last)
-static bool bank_fits(const std::vector<GridDesc> &desc, long long tensor_total) {
-    if (tensor_total > BANK_DOUBLES || desc.size() > (size_t)BANK_GRIDS) return false;
-    for (const GridDesc &gd : desc)
-        if (gd.n[gd.D - 1] > GRID_NL) return false;
-    return true;
-}
-
-static bool same_shape(const std::vector<GridDesc> &desc) {
+// Bank image of a set of grids: [tensors (already interleaved, GridDesc.tensor_off) | nodes |
+// weights].  Returns false when the plan does not qualify for the bank path.
+static bool bank_build(const std::vector<GridDesc> &desc, const std::vector<double> &il,
+                       long long tensor_total, const double *nodes_cat, const double *weights_cat,
+                       long long node_total, const int *dims_cat, const int *outputs, int smem_optin,
+                       std::vector<double> *h_bank, std::vector<BankGrid> *h_desc, size_t *smem) {
+    if (getenv("PCB_NO_BANK")) return false;
+    if (desc.size() > (size_t)BANK_GRIDS) return false;
+    int rows = 0;
     for (const GridDesc &gd : desc) {
-        if (gd.D != desc[0].D) return false;
         for (int d = 0; d < gd.D; ++d)
-            if (gd.n[d] != desc[0].n[d]) return false;
+            if (gd.n[d] > GRID_NL) return false;
+        rows = std::max(rows, gd.sum_n - gd.n[gd.D - 1]);
+    }
+    *smem = (size_t)std::max(rows, 1) * BANK_THREADS * sizeof(double);
+    if (*smem + 1024 > (size_t)smem_optin) return false;
+    long long dims_total = 0;
+    for (const GridDesc &gd : desc) dims_total += gd.D;
+    if (tensor_total + 2 * node_total + 2 * dims_total > BANK_DOUBLES) return false;
+    h_bank->assign(il.begin(), il.begin() + tensor_total);
+    h_bank->insert(h_bank->end(), nodes_cat, nodes_cat + node_total);
+    h_bank->insert(h_bank->end(), weights_cat, weights_cat + node_total);
+    h_bank->resize(h_bank->size() + 2 * dims_total);
+    double *bank_nodes = h_bank->data() + tensor_total;
+    double *bank_weights = bank_nodes + node_total;
+    double *bank_scale = bank_weights + node_total;
+    h_desc->clear();
+    int dpos = 0;
+    for (const GridDesc &gd : desc) {
+        BankGrid g;
+        memset(&g, 0, sizeof(g));
+        g.D = gd.D;
+        for (int d = 0; d < gd.D; ++d) g.n[d] = gd.n[d];
+        g.size = (int)gd.size;
+        g.tensor_off = (int)gd.tensor_off;
+        g.node_off = (int)tensor_total + gd.node_off;
+        g.weight_off = (int)(tensor_total + node_total) + gd.node_off;
+        g.scale_off = (int)(tensor_total + 2 * node_total) + 2 * dpos;
+        int off = gd.node_off;
+        for (int d = 0; d < gd.D; ++d) {
+            g.dims[d] = dims_cat ? dims_cat[dpos + d] : d;
+            // power-of-two prescale (exact): node span -> [2, 4), max |weight| -> [0.5, 1)
+            double lo = bank_nodes[off], hi = bank_nodes[off], wmax = 0.0;
+            for (int i = 0; i < gd.n[d]; ++i) {
+                lo = std::min(lo, bank_nodes[off + i]);
+                hi = std::max(hi, bank_nodes[off + i]);
+                wmax = std::max(wmax, std::fabs(bank_weights[off + i]));
+            }
+            int e = 0;
+            double sc = 1.0;
+            if (hi > lo && std::isfinite(hi - lo)) {
+                std::frexp(hi - lo, &e);  // hi - lo = f * 2^e, f in [0.5, 1)
+                sc = std::ldexp(1.0, 2 - e);
+            }
+            int ew = 0;
+            if (wmax > 0.0 && std::isfinite(wmax)) std::frexp(wmax, &ew);
+            for (int i = 0; i < gd.n[d]; ++i) {
+                bank_nodes[off + i] *= sc;
+                bank_weights[off + i] = std::ldexp(bank_weights[off + i], -ew);
+            }
+            bank_scale[2 * dpos + d] = sc;
+            bank_scale[2 * dpos + gd.D + d] = NODE_EPS * sc;
+            off += gd.n[d];
+        }
+        dpos += gd.D;
+        g.outputs = outputs ? outputs[h_desc->size()] : 1;
+        h_desc->push_back(g);
     }
     return true;
 }
 
-static int bank_acquire(int dev, uint64_t plan_id, const std::vector<double> &h_bank,
-                        const std::vector<GridDesc> &h_desc, cudaStream_t st) {
-    return g_grid_bank.acquire(dev, plan_id, st, [&](cudaStream_t s) {
+static int bank_launch(const PlanBase *pl, uint64_t plan_id, const std::vector<double> &h_bank,
+                       const std::vector<BankGrid> &h_desc, const void *kernel, void **args,
+                       size_t smem, int64_t N, cudaStream_t st) {
+    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (N + BANK_THREADS - 1) / BANK_THREADS;
+    PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
+    const int rc = g_grid_bank.acquire(pl->dev, plan_id, st, [&](cudaStream_t s) {
         cudaError_t e = cudaMemcpyToSymbolAsync(c_grid, h_bank.data(), h_bank.size() * sizeof(double), 0,
                                                 cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return e;
-        return cudaMemcpyToSymbolAsync(c_gdesc, h_desc.data(), h_desc.size() * sizeof(GridDesc), 0,
+        return cudaMemcpyToSymbolAsync(c_bgrid, h_desc.data(), h_desc.size() * sizeof(BankGrid), 0,
                                        cudaMemcpyHostToDevice, s);
     });
+    if (rc) return rc;
+    const cudaError_t e = cudaLaunchKernel(kernel, dim3((unsigned)blocks), dim3(BANK_THREADS), args, smem, st);
+    g_grid_bank.release(pl->dev, st);
+    g_launches.fetch_add(1);
+    PCB_CUDA(e);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
 }
 
 template <typename T>
@@ -428,11 +676,9 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
         grid_interleave(piece_tensors_host + (size_t)p * G, G, pl->GB, desc[p].size,
                         il.data() + desc[p].tensor_off);
     pl->plan_id = next_plan_id();
-    pl->bank_ok = bank_fits(desc, tensor_total) && same_shape(desc) && !getenv("PCB_NO_BANK");
-    if (pl->bank_ok) {
-        pl->h_bank = il;
-        pl->h_desc = desc;
-    }
+    // (pieces of different shapes are fine for the bank kernel; P <= 32 for its presence mask)
+    pl->bank_ok = bank_build(desc, il, tensor_total, piece_nodes_cat, piece_weights_cat, node_total,
+                             nullptr, nullptr, pl->smem_optin, &pl->h_bank, &pl->h_desc, &pl->bank_smem);
     DeviceGuard guard(dev);
     bool ok = guard.ok && upload(&pl->d_num_knots, meta.data(), meta.size()) &&
               upload(&pl->d_knots, knots_cat, (size_t)total_knots) &&
@@ -479,25 +725,15 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
     PCB_REQUIRE(d_points && d_out, "null device pointer");
     DeviceGuard guard(pl->dev);
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
-    if (smem > (size_t)pl->smem_optin)
+    if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
     if (pl->bank_ok) {
-        const void *uk = GRID_KERNEL_TABLE(spline_uniform_kernel, pl->GB, grid_pick_dm(pl->D));
-        PCB_CUDA(cudaFuncSetAttribute(uk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t blocks = (N + PW_THREADS - 1) / PW_THREADS;
-        PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
-        cudaStream_t st = static_cast<cudaStream_t>(stream);
-        if (int rc = bank_acquire(pl->dev, pl->plan_id, pl->h_bank, pl->h_desc, st)) return rc;
+        const void *uk = GRID_KERNEL_TABLE(spline_bank_kernel, pl->GB, grid_pick_dm(pl->D));
         void *uargs[] = {(void *)&pl->D, (void *)&pl->G, (void *)&pl->P, (void *)&pl->d_num_knots,
-                         (void *)&pl->d_knot_off, (void *)&pl->d_knots, (void *)&pl->d_nodes,
-                         (void *)&pl->d_weights, (void *)&d_points, (void *)&N, (void *)&d_out,
-                         (void *)&d_piece};
-        const cudaError_t e = cudaLaunchKernel(uk, dim3((unsigned)blocks), dim3(PW_THREADS), uargs, smem, st);
-        g_grid_bank.release(pl->dev, st);
-        g_launches.fetch_add(1);
-        PCB_CUDA(e);
-        PCB_CUDA(cudaGetLastError());
-        return PCB_OK;
+                         (void *)&pl->d_knot_off, (void *)&pl->d_knots, (void *)&d_points, (void *)&N,
+                         (void *)&d_out, (void *)&d_piece};
+        return bank_launch(pl, pl->plan_id, pl->h_bank, pl->h_desc, uk, uargs, pl->bank_smem, N,
+                           static_cast<cudaStream_t>(stream));
     }
     const void *kernel = GRID_KERNEL_TABLE(spline_eval_kernel, pl->GB, grid_pick_dm(pl->D));
     int grid = 0;
@@ -619,11 +855,8 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
             grid_interleave(outs[s].data(), slide_G[s], pl->GB, desc[s].size,
                             il.data() + desc[s].tensor_off);
     pl->plan_id = next_plan_id();
-    pl->bank_ok = bank_fits(desc, tensor_total) && !getenv("PCB_NO_BANK");
-    if (pl->bank_ok) {
-        pl->h_bank = il;
-        pl->h_desc = desc;
-    }
+    pl->bank_ok = bank_build(desc, il, tensor_total, slide_nodes_cat, slide_weights_cat, node_total,
+                             group_dims_cat, slide_G.data(), pl->smem_optin, &pl->h_bank, &pl->h_desc, &pl->bank_smem);
     std::vector<int> ints(group_off);
     for (int i = 0; i < gpos; ++i) ints.push_back(group_dims_cat[i]);
     for (int g = 0; g < G; ++g) ints.push_back(out_slide[g]);
@@ -660,25 +893,15 @@ extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64
     PCB_REQUIRE(d_points && d_out, "null device pointer");
     DeviceGuard guard(pl->dev);
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
-    if (smem > (size_t)pl->smem_optin)
+    if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
     if (pl->bank_ok) {
-        const void *uk = GRID_KERNEL_TABLE(slider_uniform_kernel, pl->GB, grid_pick_dm(pl->max_D));
-        PCB_CUDA(cudaFuncSetAttribute(uk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t blocks = (N + PW_THREADS - 1) / PW_THREADS;
-        PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
-        cudaStream_t st = static_cast<cudaStream_t>(stream);
-        if (int rc = bank_acquire(pl->dev, pl->plan_id, pl->h_bank, pl->h_desc, st)) return rc;
+        const void *uk = GRID_KERNEL_TABLE(slider_bank_kernel, pl->GB, grid_pick_dm(pl->max_D));
         void *uargs[] = {(void *)&pl->D, (void *)&pl->S, (void *)&pl->G, (void *)&pl->pivot,
-                         (void *)&pl->d_ints, (void *)&pl->d_group_dims, (void *)&pl->d_out_slide,
-                         (void *)&pl->d_row_out, (void *)&pl->d_slide_G, (void *)&pl->d_nodes,
-                         (void *)&pl->d_weights, (void *)&d_points, (void *)&N, (void *)&d_out};
-        const cudaError_t e = cudaLaunchKernel(uk, dim3((unsigned)blocks), dim3(PW_THREADS), uargs, smem, st);
-        g_grid_bank.release(pl->dev, st);
-        g_launches.fetch_add(1);
-        PCB_CUDA(e);
-        PCB_CUDA(cudaGetLastError());
-        return PCB_OK;
+                         (void *)&pl->d_out_slide, (void *)&pl->d_row_out, (void *)&d_points, (void *)&N,
+                         (void *)&d_out};
+        return bank_launch(pl, pl->plan_id, pl->h_bank, pl->h_desc, uk, uargs, pl->bank_smem, N,
+                           static_cast<cudaStream_t>(stream));
     }
     const void *kernel = GRID_KERNEL_TABLE(slider_eval_kernel, pl->GB, grid_pick_dm(pl->max_D));
     int grid = 0;

@@ -273,7 +273,9 @@ def test_spline_eval_batch_matches_reference(name):
     for r, o in enumerate(g["orders"]):
         scale_close(got[:, r], g["values"][:, r], f"{name} order={o}", factor=fac)
         one = sp.eval_batch(g["points"], [int(v) for v in o])
-        assert np.array_equal(one, got[:, r]) or np.allclose(one, got[:, r], rtol=1e-13, atol=0)
+        # the single-order call may take another kernel (constant-bank vs. global-memory
+        # evaluator): it is held to the reference like the multi-order call, not to bit equality
+        scale_close(one, g["values"][:, r], f"{name} order={o} (single)", factor=fac)
 
 
 def test_spline_single_point_knot_rule():
