@@ -332,6 +332,15 @@ def run_ours(args, rank, local_rank, world):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_bytes = 8.0 * (D + G)
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            cap = json.load(f)["ttc_fd_shared_kernel"]
+        if args.algo == 2 and plan.info()["uniform_path_fd"]:
+            traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["queries"] * n
+    except Exception:  # noqa: BLE001
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -351,7 +360,9 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks.summary(),
         "roofline": {
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf, "traffic": None,
+            "frac": achieved_tf / peak_tf, "traffic": traffic,
+            "traffic_note": "bytes per launch = ncu dram read+write per query (profiles/r1_traffic.json, "
+                            "67.8 B vs 72 B algorithmic) x queries per launch",
             "kernel": ("tt_fd_general_kernel" if args.algo == 1 else
                        ("ttc_fd_shared_kernel (cores in the constant bank, LDCU -> DFMA)"
                         if plan.info()["uniform_path_fd"] else "tt_fd_shared_kernel")),

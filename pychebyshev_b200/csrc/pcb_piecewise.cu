@@ -172,6 +172,12 @@ slider_eval_kernel(int D, int S, int G, double pivot, const GridDesc *__restrict
 //     store the result (predicated store, no branch around the math).
 // ---------------------------------------------------------------------------------------------
 constexpr int BANK_THREADS = 256;
+constexpr int BANK_MAXD = 4;  // deeper grids of <= 7808 doubles have <= 4 nodes per dim: not worth the build time
+// (GB, DM) instantiation of a bank kernel, DM in {2, 3, 4}
+#define BANK_KERNEL_TABLE(K, gb, dm)                                                              \
+    ((gb) == 4 ? ((dm) == 2 ? (const void *)K<4, 2> : (dm) == 3 ? (const void *)K<4, 3> : (const void *)K<4, 4>) \
+     : (gb) == 2 ? ((dm) == 2 ? (const void *)K<2, 2> : (dm) == 3 ? (const void *)K<2, 3> : (const void *)K<2, 4>) \
+                 : ((dm) == 2 ? (const void *)K<1, 2> : (dm) == 3 ? (const void *)K<1, 3> : (const void *)K<1, 4>))
 constexpr int BANK_DOUBLES = 7808;  // 61 KB of tensors + nodes + weights (+ 2.75 KB descriptors)
 constexpr int BANK_GRIDS = 32;      // also the width of the spline kernel's piece-presence mask
 __constant__ double c_grid[BANK_DOUBLES];
@@ -361,8 +367,7 @@ __device__ __forceinline__ void bank_contract(const BankGrid &g, int b, const do
 #pragma unroll
     for (int j = 0; j < GB; ++j) out[j] = 0.0;
     switch (g.D) {
-        BANK_CASE(1) BANK_CASE(2) BANK_CASE(3) BANK_CASE(4) BANK_CASE(5) BANK_CASE(6) BANK_CASE(7)
-        BANK_CASE(8)
+        BANK_CASE(1) BANK_CASE(2) BANK_CASE(3) BANK_CASE(4)
     }
     if (g.D == 1) {
 #pragma unroll
@@ -499,6 +504,7 @@ static bool bank_build(const std::vector<GridDesc> &desc, const std::vector<doub
     if (desc.size() > (size_t)BANK_GRIDS) return false;
     int rows = 0;
     for (const GridDesc &gd : desc) {
+        if (gd.D > BANK_MAXD) return false;
         for (int d = 0; d < gd.D; ++d)
             if (gd.n[d] > GRID_NL) return false;
         rows = std::max(rows, gd.sum_n - gd.n[gd.D - 1]);
@@ -728,7 +734,7 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
     if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
     if (pl->bank_ok) {
-        const void *uk = GRID_KERNEL_TABLE(spline_bank_kernel, pl->GB, grid_pick_dm(pl->D));
+        const void *uk = BANK_KERNEL_TABLE(spline_bank_kernel, pl->GB, grid_pick_dm(pl->D));
         void *uargs[] = {(void *)&pl->D, (void *)&pl->G, (void *)&pl->P, (void *)&pl->d_num_knots,
                          (void *)&pl->d_knot_off, (void *)&pl->d_knots, (void *)&d_points, (void *)&N,
                          (void *)&d_out, (void *)&d_piece};
@@ -896,7 +902,7 @@ extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64
     if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
     if (pl->bank_ok) {
-        const void *uk = GRID_KERNEL_TABLE(slider_bank_kernel, pl->GB, grid_pick_dm(pl->max_D));
+        const void *uk = BANK_KERNEL_TABLE(slider_bank_kernel, pl->GB, grid_pick_dm(pl->max_D));
         void *uargs[] = {(void *)&pl->D, (void *)&pl->S, (void *)&pl->G, (void *)&pl->pivot,
                          (void *)&pl->d_out_slide, (void *)&pl->d_row_out, (void *)&d_points, (void *)&N,
                          (void *)&d_out};

@@ -79,8 +79,8 @@ def kernel(rep, out):
                 if len(r) <= max(si, ni, xi):
                     continue
                 toks = r[si].split()
-                if not toks:
-                    continue
+                if not toks or not (r[xi] or '0').isdigit() or not (r[ni] or '0').isdigit():
+                    continue  # blank line or a repeated header (several launches in one report)
                 op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
                 ops[op] += int(r[xi] or 0)
                 samples[op] += int(r[ni] or 0)
