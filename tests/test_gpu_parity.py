@@ -320,6 +320,131 @@ def test_slider_matches_reference():
 
 
 # ------------------------------------------------------------------------------------------
+# constant-bank evaluators (uniform datapath) against the global-memory evaluators
+# ------------------------------------------------------------------------------------------
+
+def _both_paths(make, monkeypatch):
+    """The same object twice: plans on the constant-bank path and (PCB_NO_BANK) on the generic one."""
+    bank = make()
+    monkeypatch.setenv("PCB_NO_BANK", "1")
+    generic = make()
+    generic._plans = {}
+    return bank, generic
+
+
+@pytest.mark.parametrize("name", ["spline_abs1d", "spline_bs2d", "spline_multiknot3d"])
+def test_spline_bank_and_generic_evaluators_agree(name, monkeypatch):
+    g, _ = _spline(name)
+    bank, generic = _both_paths(lambda: _spline(name)[1], monkeypatch)
+    dom = np.asarray(g["domain"], dtype=np.float64)
+    D = len(dom)
+    rng = np.random.default_rng(11)
+    knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+    for n in (1, 255, 257, 100_003):  # ragged: no multiple of the 256-query CTA tile
+        pts = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.random((n, D))
+        if n > 64:
+            # node hits (one-hot rows), knots (right-hand piece) and the domain corners
+            nodes0 = pieces[0][1]
+            pts[3] = [nodes0[d][min(1, len(nodes0[d]) - 1)] for d in range(D)]
+            pts[4] = dom[:, 0]
+            pts[5] = dom[:, 1]
+            for d in range(D):
+                if len(knots[d]):
+                    pts[6 + d, d] = knots[d][0]
+        a = bank.eval_batch(pts, [0] * D)
+        b = generic.eval_batch(pts, [0] * D)
+        assert np.array_equal(bank.find_pieces(pts), generic.find_pieces(pts))
+        tol = 1e-12 * max(1.0, float(np.max(np.abs(b)))) + 1e-14
+        assert np.max(np.abs(a - b)) <= tol, (name, n, float(np.max(np.abs(a - b))))
+        if n > 64:
+            # exact node hit of piece 0: the tensor entry itself, on both paths
+            want = pieces[0][0][tuple(min(1, len(nodes0[d]) - 1) for d in range(D))]
+            assert a[3] == want and b[3] == want
+    # NaN coordinates: NaN out, routed to the last piece (spline.py:677-690), no trap
+    pts = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.random((40, D))
+    pts[7, 0] = np.nan
+    a, b = bank.eval_batch(pts, [0] * D), generic.eval_batch(pts, [0] * D)
+    assert np.isnan(a[7]) and np.isnan(b[7])
+    keep = np.arange(40) != 7
+    assert np.allclose(a[keep], b[keep], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("width", [1e-3, 1.0, 1e6, 1e20])
+def test_spline_bank_path_any_domain_width(width, monkeypatch):
+    """The product-form rows are prescaled by powers of two: no overflow for any domain width.
+    (Much narrower domains hit the reference's ABSOLUTE 1e-14 node-snap threshold, much wider ones
+    underflow the reference's own barycentric weights: neither is an evaluator property.)"""
+    import pychebyshev_b200 as pcb
+    from pychebyshev_b200 import _grid
+
+    dom = [[-0.25 * width, 0.75 * width], [2.0 * width, 3.0 * width]]
+    n = [15, 16]
+    knots = [[0.1 * width], []]
+
+    def f(x, y):
+        return np.cos(3.0 * x / width) * (y / width) ** 2
+
+    def make():
+        sp = pcb.ChebyshevSpline(None, 2, dom, n, knots, defer_build=True)
+        for piece in sp._pieces:
+            xs, ys = np.meshgrid(piece.nodes[0], piece.nodes[1], indexing="ij")
+            piece.set_original_function_values(f(xs, ys))
+        sp._built = True
+        return sp
+
+    bank, generic = _both_paths(make, monkeypatch)
+    rng = np.random.default_rng(5)
+    lo = np.array([d[0] for d in dom])
+    hi = np.array([d[1] for d in dom])
+    pts = lo + (hi - lo) * rng.random((5000, 2))
+    a, b = bank.eval_batch(pts, [0, 0]), generic.eval_batch(pts, [0, 0])
+    exact = f(pts[:, 0], pts[:, 1])
+    assert np.all(np.isfinite(a))
+    assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b)) + 1e-14
+    assert np.max(np.abs(a - exact)) <= 1e-9 * np.max(np.abs(exact))  # interpolation error, both paths
+    del _grid
+
+
+def test_slider_bank_and_generic_evaluators_agree(monkeypatch):
+    import pychebyshev_b200 as pcb
+
+    g = G.load("slider10d")
+    part, pivot_value, slides = G.slider_parts(g, O.diff_matrix)
+    dom = [list(map(float, r)) for r in g["domain"]]
+    n = [int(v) for v in g["n_nodes"]]
+
+    def make():
+        return pcb.ChebyshevSlider.from_slides([s[0] for s in slides], 10, dom, n, part,
+                                               list(g["pivot_point"]), pivot_value)
+
+    bank, generic = _both_paths(make, monkeypatch)
+    rng = np.random.default_rng(3)
+    lo = np.array([d[0] for d in dom])
+    hi = np.array([d[1] for d in dom])
+    # 7 rows: more than the 4 the bank kernel keeps in registers (the rest go through global memory)
+    orders = [[0] * 10]
+    for d in (0, 3, 4, 9):
+        o = [0] * 10
+        o[d] = 1
+        orders.append(o)
+    o = [0] * 10
+    o[0], o[9] = 1, 1  # cross-slide: exactly zero
+    orders.append(o)
+    o = [0] * 10
+    o[2] = 2
+    orders.append(o)
+    for rows in (1, 300, 70_001):
+        pts = lo + (hi - lo) * rng.random((rows, 10))
+        a = bank.eval_batch_multi(pts, orders)
+        b = generic.eval_batch_multi(pts, orders)
+        assert a.shape == (rows, len(orders))
+        assert np.array_equal(a[:, 5], np.zeros(rows)) and np.array_equal(b[:, 5], np.zeros(rows))
+        for r in range(len(orders)):
+            tol = 2e-11 * max(1.0, float(np.max(np.abs(b[:, r])))) + 1e-14
+            assert np.max(np.abs(a[:, r] - b[:, r])) <= tol, (rows, r)
+
+
+# ------------------------------------------------------------------------------------------
 # size-independent properties at scale (BASELINE sizes do not fit a CPU oracle)
 # ------------------------------------------------------------------------------------------
 
