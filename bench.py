@@ -288,6 +288,13 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- end to end through the host-buffer API ---------------------------------------------
     e2e_n = min(n, args.e2e_queries)
+    try:  # all ranks pin their host buffers on one box: stay well inside its free memory
+        import psutil
+
+        cap = int(0.4 * psutil.virtual_memory().available / max(1, world) / (8 * (D + G)))
+        e2e_n = max(1_000_000, min(e2e_n, cap))
+    except Exception:  # noqa: BLE001
+        pass
     h_pts = _engine.pinned_empty((e2e_n, D))
     h_out = _engine.pinned_empty((e2e_n, G))
     torch.from_numpy(h_pts).copy_(pts[:e2e_n])
