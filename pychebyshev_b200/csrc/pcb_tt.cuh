@@ -14,6 +14,9 @@
 // ahead).
 #pragma once
 
+#include <map>
+#include <mutex>
+
 #include "pcb_common.cuh"
 
 namespace pcb {
@@ -83,8 +86,22 @@ struct TTPlan : PlanBase {
     // values need the forward cores, the shared-FD kernel the transposed copies as well
     bool const_value_ok = false, const_shared_ok = false;
     int const_qpt = 2, const_threads_value = 512, const_threads_shared = 512;
-    uint64_t plan_id = 0;
-    std::vector<double> h_const;  // [forward unpadded | transposed unpadded]
+    // Constant-bank images (pcb_tt_const.cu).  The 8192-double bank holds only the cores a launch
+    // reads: all forward cores for values; for price+Greeks the forward cores left of the last
+    // differentiated dim, the transposed cores right of the first, and each differentiated core in
+    // the orientation its coefficient pass uses.  One image per distinct need, built on first use.
+    struct ConstImage {
+        uint64_t id = 0;  // ConstBank residency key
+        std::vector<double> data;
+        int coff[PCB_MAX_DIMS], coffT[PCB_MAX_DIMS];
+    };
+    bool const_enabled = false;
+    std::vector<double> h_fwd, h_T;  // unpadded cores, forward and transposed, same offsets
+    int core_off[PCB_MAX_DIMS + 1] = {0};
+    std::mutex image_mutex;
+    std::map<uint64_t, ConstImage> images;  // key: need_fwd mask | need_T mask << 32
+    bool last_fd_const = false;
+    const ConstImage *const_image(uint64_t need_fwd, uint64_t need_T);
     ~TTPlan() override;
 };
 
@@ -107,9 +124,11 @@ int tt_launch_general(const TTPlan *pl, const TTFdProgram &prog, const double *d
 int tt_launch_shared(const TTPlan *pl, const TTSharedProgram &prog, const double *d_points,
                      int64_t N, double *d_out, cudaStream_t st);
 void ttc_forget(const TTPlan *pl);
-int ttc_launch_value(const TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st);
-int ttc_launch_shared(const TTPlan *pl, const TTSharedProgram &prog, const double *d_points,
-                      int64_t N, double *d_out, cudaStream_t st);
+// constant-bank launches; *fits = false (and nothing launched) when the needed cores exceed the bank
+int ttc_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st,
+                     bool *fits);
+int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
+                      double *d_out, cudaStream_t st, bool *fits);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

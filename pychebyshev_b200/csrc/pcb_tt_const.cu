@@ -254,13 +254,47 @@ ttc_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-static ConstBank g_bank;  // residency of one plan per device in c_tt (pcb_cbank.cuh)
+static ConstBank g_bank;  // residency of one image per device in c_tt (pcb_cbank.cuh)
 
-void ttc_forget(const TTPlan *pl) { g_bank.forget(pl->dev, pl->plan_id); }
+void ttc_forget(const TTPlan *pl) {
+    for (const auto &kv : pl->images) g_bank.forget(pl->dev, kv.second.id);
+}
+
+// The image holding forward cores `need_fwd` and transposed cores `need_T` (bit k = core k), or
+// nullptr when they do not fit in the bank.
+const TTPlan::ConstImage *TTPlan::const_image(uint64_t need_fwd, uint64_t need_T) {
+    if (!const_enabled) return nullptr;
+    std::lock_guard<std::mutex> lock(image_mutex);
+    const uint64_t key = need_fwd | (need_T << 32);
+    auto it = images.find(key);
+    if (it != images.end()) return it->second.data.empty() ? nullptr : &it->second;
+    ConstImage &img = images[key];
+    size_t total = 0;
+    for (int k = 0; k < P.D; ++k) {
+        const size_t sz = (size_t)(core_off[k + 1] - core_off[k]);
+        total += ((need_fwd >> k) & 1 ? sz : 0) + ((need_T >> k) & 1 ? sz : 0);
+    }
+    if (total > (size_t)TT_CONST_MAX) return nullptr;  // remembered as an empty image
+    img.id = next_plan_id();
+    img.data.reserve(total);
+    for (int k = 0; k < P.D; ++k) {
+        img.coff[k] = img.coffT[k] = 0;
+        if ((need_fwd >> k) & 1) {
+            img.coff[k] = (int)img.data.size();
+            img.data.insert(img.data.end(), h_fwd.begin() + core_off[k], h_fwd.begin() + core_off[k + 1]);
+        }
+    }
+    for (int k = 0; k < P.D; ++k)
+        if ((need_T >> k) & 1) {
+            img.coffT[k] = (int)img.data.size();
+            img.data.insert(img.data.end(), h_T.begin() + core_off[k], h_T.begin() + core_off[k + 1]);
+        }
+    return &img;
+}
 
 template <typename K, typename... Args>
-static int ttc_launch(K kernel, const TTPlan *pl, int qpt, int threads, int nbuf, int64_t N,
-                      cudaStream_t st, Args... args) {
+static int ttc_launch(K kernel, const TTPlan *pl, const TTPlan::ConstImage *img, int qpt, int threads,
+                      int nbuf, int64_t N, cudaStream_t st, Args... args) {
     const size_t smem = (size_t)nbuf * pl->P.rmaxp * qpt * threads * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "TT uniform-path kernel needs %zu B of shared memory", smem);
@@ -269,9 +303,9 @@ static int ttc_launch(K kernel, const TTPlan *pl, int qpt, int threads, int nbuf
     const int64_t ntiles = (N + tile - 1) / tile;
     if (ntiles > 0x7fffffffLL)
         return fail(PCB_EINVAL, "batch of %lld queries is too large for one launch", (long long)N);
-    if (int rc = g_bank.acquire(pl->dev, pl->plan_id, st, [&](cudaStream_t s) {
-            return cudaMemcpyToSymbolAsync(c_tt, pl->h_const.data(), pl->h_const.size() * sizeof(double),
-                                           0, cudaMemcpyHostToDevice, s);
+    if (int rc = g_bank.acquire(pl->dev, img->id, st, [&](cudaStream_t s) {
+            return cudaMemcpyToSymbolAsync(c_tt, img->data.data(), img->data.size() * sizeof(double), 0,
+                                           cudaMemcpyHostToDevice, s);
         }))
         return rc;
     kernel<<<(int)ntiles, threads, smem, st>>>(args...);
@@ -289,29 +323,100 @@ static int ttc_rank_class(const TTPlan *pl) {
     return rmax <= 8 ? 8 : (rmax <= 12 ? 12 : 16);
 }
 
+// the kernel's view of the plan: core offsets of THIS image
+static TTParams ttc_params(const TTPlan *pl, const TTPlan::ConstImage *img) {
+    TTParams P = pl->P;
+    for (int k = 0; k < P.D; ++k) {
+        P.coff[k] = img->coff[k];
+        P.coffT[k] = img->coffT[k];
+    }
+    return P;
+}
+
 #define TTC_VALUE(Q, R)                                                                           \
     if (pl->const_qpt == Q && rc_ == R)                                                           \
-        return ttc_launch(ttc_value_kernel<Q, R, 512>, pl, Q, threads, 1, N, st, pl->P, d_points, N, \
+        return ttc_launch(ttc_value_kernel<Q, R, 512>, pl, img, Q, threads, 1, N, st, P, d_points, N, \
                           d_out);
 #define TTC_SHARED(Q, R, T)                                                                       \
     if (pl->const_qpt == Q && rc_ == R && threads <= T)                                           \
-        return ttc_launch(ttc_fd_shared_kernel<Q, R, T>, pl, Q, threads, 2, N, st, pl->P, prog,     \
+        return ttc_launch(ttc_fd_shared_kernel<Q, R, T>, pl, img, Q, threads, 2, N, st, P, prog,    \
                           d_points, N, d_out);
 
-int ttc_launch_value(const TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+int ttc_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st,
+                     bool *fits) {
+    const uint64_t all = pl->P.D >= 32 ? 0xffffffffull : ((1ull << pl->P.D) - 1);
+    const TTPlan::ConstImage *img = pl->const_image(all, 0);
+    *fits = img != nullptr;
+    if (!img) return PCB_OK;
+    const TTParams P = ttc_params(pl, img);
     const int threads = pl->const_threads_value, rc_ = ttc_rank_class(pl);
     TTC_VALUE(2, 8) TTC_VALUE(2, 12) TTC_VALUE(2, 16) TTC_VALUE(1, 8) TTC_VALUE(1, 12) TTC_VALUE(1, 16)
     return fail(PCB_EUNSUPPORTED, "no uniform-path TT value kernel for this configuration");
 }
 
-int ttc_launch_shared(const TTPlan *pl, const TTSharedProgram &prog, const double *d_points,
-                      int64_t N, double *d_out, cudaStream_t st) {
-    const int threads = pl->const_threads_shared, rc_ = ttc_rank_class(pl);
+// cores ttc_fd_shared_kernel reads for `prog`: left sweep up to the last slot, right sweeps down to
+// the first, each slot's own core in the orientation of its coefficient pass
+static void ttc_shared_need(const TTPlan *pl, const TTSharedProgram &prog, uint64_t *need_fwd,
+                            uint64_t *need_T) {
+    *need_fwd = *need_T = 0;
+    const int a_min = prog.slot_dim[0], a_max = prog.slot_dim[prog.n_slots - 1];
+    for (int k = 0; k < a_max; ++k) *need_fwd |= 1ull << k;
+    for (int k = a_min + 1; k < pl->P.D; ++k) *need_T |= 1ull << k;
+    for (int t = 0; t < prog.n_slots; ++t) {
+        const int a = prog.slot_dim[t];
+        if (pl->P.r[a + 1] >= pl->P.r[a])
+            *need_fwd |= 1ull << a;
+        else
+            *need_T |= 1ull << a;
+    }
+}
+
+static int ttc_launch_shared_one(TTPlan *pl, const TTPlan::ConstImage *img, const TTSharedProgram &prog,
+                                 const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+    // both chain-vector buffers must fit in shared memory
+    int threads = pl->const_threads_shared;
+    while ((size_t)2 * pl->P.rmaxp * pl->const_qpt * threads * 8 > (size_t)pl->smem_optin && threads > 128)
+        threads -= 128;
+    const TTParams P = ttc_params(pl, img);
+    const int rc_ = ttc_rank_class(pl);
     TTC_SHARED(2, 8, 256) TTC_SHARED(2, 12, 256) TTC_SHARED(2, 16, 256)
     TTC_SHARED(2, 8, 384) TTC_SHARED(2, 12, 384) TTC_SHARED(2, 16, 384)
     TTC_SHARED(2, 8, 512) TTC_SHARED(2, 12, 512) TTC_SHARED(2, 16, 512)
     TTC_SHARED(1, 8, 512) TTC_SHARED(1, 12, 512) TTC_SHARED(1, 16, 512)
     return fail(PCB_EUNSUPPORTED, "no uniform-path TT shared-FD kernel for this configuration");
+}
+
+int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
+                      double *d_out, cudaStream_t st, bool *fits) {
+    uint64_t need_fwd, need_T;
+    ttc_shared_need(pl, prog, &need_fwd, &need_T);
+    const TTPlan::ConstImage *img = pl->const_image(need_fwd, need_T);
+    *fits = img != nullptr;
+    if (img) return ttc_launch_shared_one(pl, img, prog, d_points, N, d_out, st);
+    if (prog.n_slots < 2) return PCB_OK;
+    // The union does not fit (Greeks at both ends of a long train need every core in both
+    // orientations): one launch per differentiated dim, each with its own image and writing only
+    // its own output rows (value rows go with the first).  Left sweeps restart per launch.
+    constexpr int SKIP = 1 << 20;  // row_slot that matches no slot and is not a value row
+    TTSharedProgram sub[TT_MAX_G];
+    const TTPlan::ConstImage *imgs[TT_MAX_G];
+    for (int t = 0; t < prog.n_slots; ++t) {
+        sub[t].G = prog.G;
+        sub[t].n_slots = 1;
+        sub[t].slot_dim[0] = prog.slot_dim[t];
+        for (int g = 0; g < prog.G; ++g) {
+            const int rs = prog.row_slot[g];
+            sub[t].row_slot[g] = rs == t ? 0 : ((rs < 0 && t == 0) ? -1 : SKIP);
+            sub[t].row_ord[g] = prog.row_ord[g];
+        }
+        ttc_shared_need(pl, sub[t], &need_fwd, &need_T);
+        imgs[t] = pl->const_image(need_fwd, need_T);
+        if (!imgs[t]) return PCB_OK;  // *fits stays false: shared-memory kernel
+    }
+    *fits = true;
+    for (int t = 0; t < prog.n_slots; ++t)
+        if (int rc = ttc_launch_shared_one(pl, imgs[t], sub[t], d_points, N, d_out, st)) return rc;
+    return PCB_OK;
 }
 
 }  // namespace pcb

@@ -184,40 +184,35 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
                 }
             }
     }
-    // uniform-datapath path: unpadded forward (+ transposed) cores for the constant bank
+    // uniform-datapath path: unpadded forward and transposed cores, packed per launch need into
+    // constant-bank images (TTPlan::const_image)
     {
-        pl->plan_id = next_plan_id();
         int fwd = 0, rmax = 1;
         for (int k = 0; k < D; ++k) {
-            P.coff[k] = fwd;
+            pl->core_off[k] = fwd;
             fwd += ranks[k] * n[k] * ranks[k + 1];
             if (ranks[k + 1] > rmax) rmax = ranks[k + 1];
         }
-        for (int k = 0; k < D; ++k) P.coffT[k] = fwd + P.coff[k];  // same sizes, same order
-        const bool enabled = env_int("PCB_TT_CONST", 1) != 0 && rmax <= TT_CONST_MAX_RANK;
-        pl->const_value_ok = enabled && fwd <= TT_CONST_MAX;
-        pl->const_shared_ok = enabled && 2 * fwd <= TT_CONST_MAX;
-        if (pl->const_value_ok) {
-            pl->h_const.assign(cores_cat, cores_cat + fwd);
-            if (pl->const_shared_ok) {
-                pl->h_const.resize(2 * (size_t)fwd);
-                size_t s2 = 0;
-                for (int k = 0; k < D; ++k)
-                    for (int i = 0; i < ranks[k]; ++i)
-                        for (int j = 0; j < n[k]; ++j)
-                            for (int l = 0; l < ranks[k + 1]; ++l)
-                                pl->h_const[(size_t)P.coffT[k] + ((size_t)l * n[k] + j) * ranks[k] + i] =
-                                    cores_cat[s2++];
-            }
+        pl->core_off[D] = fwd;
+        pl->const_enabled = env_int("PCB_TT_CONST", 1) != 0 && rmax <= TT_CONST_MAX_RANK;
+        pl->const_value_ok = pl->const_enabled && fwd <= TT_CONST_MAX;
+        pl->const_shared_ok = pl->const_enabled && 2 * fwd <= TT_CONST_MAX;  // any Greek set fits
+        if (pl->const_enabled) {
+            pl->h_fwd.assign(cores_cat, cores_cat + fwd);
+            pl->h_T.resize((size_t)fwd);
+            size_t s2 = 0;
+            for (int k = 0; k < D; ++k)
+                for (int i = 0; i < ranks[k]; ++i)
+                    for (int j = 0; j < n[k]; ++j)
+                        for (int l = 0; l < ranks[k + 1]; ++l)
+                            pl->h_T[(size_t)pl->core_off[k] + ((size_t)l * n[k] + j) * ranks[k] + i] =
+                                cores_cat[s2++];
             pl->const_qpt = env_int("PCB_TT_QPT", 2) == 1 ? 1 : 2;
             const int t = env_int("PCB_TT_THREADS", 512);
             pl->const_threads_value = t;
             pl->const_threads_shared = t;
-            // the two chain-vector buffers of the shared-FD kernel must fit in shared memory
-            while ((size_t)2 * P.rmaxp * pl->const_qpt * pl->const_threads_shared * 8 >
-                       (size_t)pl->smem_optin && pl->const_threads_shared > 128)
-                pl->const_threads_shared -= 128;
         }
+        pl->last_fd_const = pl->const_shared_ok;
     }
     if (int rc = tt_pick_cfg(pl, false, &pl->cfg_chain)) {
         delete pl;
@@ -250,7 +245,11 @@ extern "C" PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N
     if (N == 0) return PCB_OK;
     PCB_REQUIRE(d_points && d_out, "null device pointer");
     DeviceGuard guard(pl->dev);
-    if (pl->const_value_ok) return ttc_launch_value(pl, d_points, N, d_out, static_cast<cudaStream_t>(stream));
+    if (pl->const_value_ok) {
+        bool fits = false;
+        const int rc = ttc_launch_value(pl, d_points, N, d_out, static_cast<cudaStream_t>(stream), &fits);
+        if (rc || fits) return rc;
+    }
     return tt_launch_value(pl, d_points, N, d_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -258,7 +257,7 @@ extern "C" PCB_API int pcb_tt_plan_info(void *plan, int32_t *out8) {
     TTPlan *pl = static_cast<TTPlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_TT && out8, "not a TT plan");
     out8[0] = pl->const_value_ok;
-    out8[1] = pl->const_shared_ok;
+    out8[1] = pl->last_fd_const;  // did the last price+Greeks launch run from the constant bank?
     out8[2] = pl->const_qpt;
     out8[3] = pl->const_threads_value;
     out8[4] = pl->const_threads_shared;
@@ -296,8 +295,15 @@ extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_
     PCB_REQUIRE(d_points && d_out, "null device pointer");
     DeviceGuard guard(pl->dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (algo == 2 || (algo == 0 && can_share))
-        return pl->const_shared_ok ? ttc_launch_shared(pl, sp, d_points, N, d_out, st)
-                            : tt_launch_shared(pl, sp, d_points, N, d_out, st);
+    if (algo == 2 || (algo == 0 && can_share)) {
+        // constant bank when the cores this Greek set reads fit in it, shared memory otherwise
+        bool fits = false;
+        if (pl->const_enabled) {
+            const int rc = ttc_launch_shared(pl, sp, d_points, N, d_out, st, &fits);
+            pl->last_fd_const = fits;
+            if (rc || fits) return rc;
+        }
+        return tt_launch_shared(pl, sp, d_points, N, d_out, st);
+    }
     return tt_launch_general(pl, prog, d_points, N, d_out, st);
 }
