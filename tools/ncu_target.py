@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small, deterministic launch sequence of one kernel for ncu captures.
 
-usage: ncu_target.py {tt_value|tt_fd1|tt_fd2|full_dmma|full_fma|spline|lookup} [N]
+usage: ncu_target.py {tt_value|tt_fd1|tt_fd2|full_dmma|full_fma|spline|spline_value|lookup} [N]
 """
 import os
 import sys
@@ -63,6 +63,8 @@ def main():
         pts = rand_points(wl.SPLINE2D_DOMAIN, n)
         if which == "lookup":
             fn = lambda: sp.find_pieces(pts)  # noqa: E731
+        elif which == "spline_value":
+            fn = lambda: sp.eval_batch(pts, [0, 0])  # noqa: E731
         else:
             fn = lambda: sp.eval_batch_multi(pts, [[0, 0], [1, 0]])  # noqa: E731
     for _ in range(reps):
