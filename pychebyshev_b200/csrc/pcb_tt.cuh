@@ -101,6 +101,9 @@ struct TTPlan : PlanBase {
     std::mutex image_mutex;
     std::map<uint64_t, ConstImage> images;  // key: need_fwd mask | need_T mask << 32
     bool last_fd_const = false;
+    // per-core launches with the chain state in global memory (large trains, pcb_tt_const.cu)
+    bool gstream_ok = false;
+    std::map<int, ConstImage> gimages;  // key 2 k + orientation; coff[c] chunk bases, coffT[c] widths
     const ConstImage *const_image(uint64_t need_fwd, uint64_t need_T);
     ~TTPlan() override;
 };
@@ -129,6 +132,10 @@ int ttc_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_ou
                      bool *fits);
 int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
                       double *d_out, cudaStream_t st, bool *fits);
+// one launch per core, chain state in global memory (trains whose single cores fit in the bank)
+int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st);
+int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
+                      double *d_out, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

@@ -19,6 +19,8 @@
 // the transposed cores G_k^T[l][j][i] of ONE plan per device at a time; `ttc_make_resident`
 // uploads on a plan switch, ordered against kernels of the previous plan on other streams.
 // Trains that do not fit (8192 doubles, ranks <= 16) use the shared-memory kernels.
+#include <algorithm>
+
 #include "pcb_cbank.cuh"
 #include "pcb_tt.cuh"
 
@@ -253,11 +255,245 @@ ttc_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__
     }
 }
 
+// ---- large trains: one launch per core, chain state in global memory ---------------------------------
+// A train whose cores do not fit in the bank together (10-D rank 20: 285 KB) still has cores that
+// fit one at a time (rank 20, 11 nodes: 34 KB).  The chain then runs as one launch per core with
+// the bank holding that core, and the per-query chain vector (<= 64 doubles) travels through
+// global memory between launches as planes S[l][query] (coalesced; 16 r bytes per query per core
+// against 2 r^2 n flop, far below the HBM roofline).  Output columns are processed in chunks of
+// <= 16 register accumulators; the bank image of a core is chunk-major: chunk c holds
+// [(i n + j) W_c + l].
+constexpr int TTG_MAX_CHUNKS = 4;  // ranks up to 64
+constexpr int TTG_MAX_RANK = 16 * TTG_MAX_CHUNKS;
+
+struct TTGStep {
+    int r_in, r_out, n, col, D;
+    double lo, hi;
+    int nchunks, cbase[TTG_MAX_CHUNKS], cw[TTG_MAX_CHUNKS];
+    const double *s_in;  // r_in planes, or nullptr for the vector [1]
+    double *s_out;       // r_out planes (or the output column when r_out == 1 ends a value chain)
+    int64_t pstride;     // plane stride of s_in / s_out
+    int64_t q_begin;     // first query of this tile
+};
+
+template <int W, int QPT>
+__device__ __forceinline__ void ttc_chunk_g(int base, int r_in, int n, const double *v_in, int vstride,
+                                            const double (&s)[QPT], double *g_out, int64_t pstride,
+                                            const bool (&live)[QPT]) {
+    double acc[QPT][W], twos[QPT];
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+        twos[qq] = 2.0 * s[qq];
+#pragma unroll
+        for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
+    }
+    int gp = base;
+    for (int i = 0; i < r_in; ++i) {
+        double c0[QPT], c1[QPT];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            const double vi = v_in[(i * QPT + qq) * vstride];
+            c0[qq] = vi;
+            c1[qq] = vi * s[qq];
+        }
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+#pragma unroll
+            for (int l = 0; l < W; ++l) {
+                const double gv = c_tt[gp + l];  // LDCU.64
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) acc[qq][l] = fma(c0[qq], gv, acc[qq][l]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                const double c2 = fma(twos[qq], c1[qq], -c0[qq]);
+                c0[qq] = c1[qq];
+                c1[qq] = c2;
+            }
+            gp += W;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < W; ++l)
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq)
+            if (live[qq]) g_out[l * pstride + qq * vstride] = acc[qq][l];
+}
+
+template <int QPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 512 / MAXT)
+ttc_gstep_kernel(const __grid_constant__ TTGStep a, const double *__restrict__ pts, int64_t N) {
+    constexpr int RMAX = 16;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, vstride = blockDim.x;
+    const int64_t ql0 = (int64_t)blockIdx.x * vstride * QPT + tid;  // tile-local index of slot 0
+    double s[QPT];
+    bool live[QPT];
+    double *vbuf = smem + tid;
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+        const int64_t ql = ql0 + qq * (int64_t)vstride;
+        int64_t q = a.q_begin + ql;
+        live[qq] = q < N;
+        if (!live[qq]) q = N - 1;
+        s[qq] = tt_scale(__ldg(pts + q * a.D + a.col), a.lo, a.hi);
+        if (a.s_in) {
+            for (int i = 0; i < a.r_in; ++i) vbuf[(i * QPT + qq) * vstride] = a.s_in[i * a.pstride + ql];
+        } else {
+            vbuf[qq * vstride] = 1.0;
+        }
+    }
+    // (compile-time chunk indices: a dynamically indexed kernel-parameter array lands in vector
+    // registers and takes every bank address with it off the uniform datapath)
+    int l0 = 0;
+#pragma unroll
+    for (int c = 0; c < TTG_MAX_CHUNKS; ++c) {
+        if (c < a.nchunks) {
+            const int w = a.cw[c];
+            double *g_out = a.s_out + l0 * a.pstride + ql0;
+            TTC_SWITCH(ttc_chunk_g, a.cbase[c], a.r_in, a.n, vbuf, vstride, s, g_out, a.pstride, live)
+            l0 += w;
+        }
+    }
+}
+
+struct TTGCoeff {
+    int r_rows, r_acc, n, col, D, G;
+    double lo, hi;
+    int nchunks, cbase[TTG_MAX_CHUNKS], cw[TTG_MAX_CHUNKS];
+    const double *s_rows, *s_acc;  // planes, or nullptr for the vector [1]
+    int64_t pstride, q_begin;
+    int row_kind[TT_MAX_G];  // 0 skip, -1 value row, 1 / 2 central difference of that order
+    double *out;             // (N, G) row-major
+};
+
+// y_j += sum_l (sum_i vrow[i] G[i][j][l0 + l]) vacc[l0 + l] for one chunk of the accumulated index
+template <int W, int QPT>
+__device__ __forceinline__ void ttc_ychunk(int base, int r_rows, int n, const double *v_rows,
+                                           const double *v_acc, int vstride, double *ybuf) {
+    for (int j = 0; j < n; ++j) {
+        double acc[QPT][W];
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+            for (int l = 0; l < W; ++l) acc[qq][l] = 0.0;
+        int gp = base + j * W;
+        for (int i = 0; i < r_rows; ++i) {
+            double li[QPT];
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) li[qq] = v_rows[(i * QPT + qq) * vstride];
+#pragma unroll
+            for (int l = 0; l < W; ++l) {
+                const double gv = c_tt[gp + l];
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) acc[qq][l] = fma(li[qq], gv, acc[qq][l]);
+            }
+            gp += n * W;
+        }
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+            for (int l = 0; l < W; ++l) {
+                const double va = v_acc[(l * QPT + qq) * vstride];
+                if (l & 1)
+                    y1 = fma(acc[qq][l], va, y1);
+                else
+                    y0 = fma(acc[qq][l], va, y0);
+            }
+            ybuf[(j * QPT + qq) * vstride] += y0 + y1;
+        }
+    }
+}
+
+template <int QPT, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+ttc_gcoeff_kernel(const __grid_constant__ TTGCoeff a, const double *__restrict__ pts, int64_t N) {
+    constexpr int RMAX = 16;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, vstride = blockDim.x;
+    const int64_t ql0 = (int64_t)blockIdx.x * vstride * QPT + tid;
+    double *v_rows = smem + tid;
+    double *v_acc = v_rows + (size_t)a.r_rows * QPT * vstride;
+    double *ybuf = v_acc + (size_t)a.r_acc * QPT * vstride;
+    const double h = (a.hi - a.lo) * 1e-4;
+    double sm[4][QPT];
+    bool live[QPT];
+    int64_t qg[QPT];
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+        const int64_t ql = ql0 + qq * (int64_t)vstride;
+        int64_t q = a.q_begin + ql;
+        live[qq] = q < N;
+        if (!live[qq]) q = N - 1;
+        qg[qq] = q;
+        // stencil abscissae (reference _fd_step / _nudge_point): 0 query, 1 centre c, 2 c+h, 3 c-h
+        const double x = __ldg(pts + q * a.D + a.col);
+        const double c = tt_nudge(x, a.lo, a.hi, h);
+        sm[0][qq] = tt_scale(x, a.lo, a.hi);
+        sm[1][qq] = tt_scale(c, a.lo, a.hi);
+        sm[2][qq] = tt_scale(c + h, a.lo, a.hi);
+        sm[3][qq] = tt_scale(c - h, a.lo, a.hi);
+        if (a.s_rows) {
+            for (int i = 0; i < a.r_rows; ++i) v_rows[(i * QPT + qq) * vstride] = a.s_rows[i * a.pstride + ql];
+        } else {
+            v_rows[qq * vstride] = 1.0;
+        }
+        if (a.s_acc) {
+            for (int l = 0; l < a.r_acc; ++l) v_acc[(l * QPT + qq) * vstride] = a.s_acc[l * a.pstride + ql];
+        } else {
+            v_acc[qq * vstride] = 1.0;
+        }
+        for (int j = 0; j < a.n; ++j) ybuf[(j * QPT + qq) * vstride] = 0.0;
+    }
+    int l0 = 0;
+#pragma unroll
+    for (int c = 0; c < TTG_MAX_CHUNKS; ++c) {
+        if (c < a.nchunks) {
+            const int w = a.cw[c];
+            const double *vacc_c = v_acc + (size_t)l0 * QPT * vstride;
+            TTC_SWITCH(ttc_ychunk, a.cbase[c], a.r_rows, a.n, v_rows, vacc_c, vstride, ybuf)
+            l0 += w;
+        }
+    }
+    // Clenshaw over the four abscissae: b_j = y_j + 2 s b_{j+1} - b_{j+2}, f = b_0 - s b_1
+    double b1[4][QPT], b2[4][QPT];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) b1[m][qq] = b2[m][qq] = 0.0;
+    for (int j = a.n - 1; j >= 0; --j) {
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            const double y = ybuf[(j * QPT + qq) * vstride];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const double bn = fma(2.0 * sm[m][qq], b1[m][qq], y - b2[m][qq]);
+                b2[m][qq] = b1[m][qq];
+                b1[m][qq] = bn;
+            }
+        }
+    }
+    for (int g = 0; g < a.G; ++g) {
+        const int kind = a.row_kind[g];
+        if (kind == 0) continue;
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq) {
+            double f[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) f[m] = fma(-sm[m][qq], b2[m][qq], b1[m][qq]);
+            const double res = kind < 0 ? f[0] : tt_fd_reduce(kind, f[2], f[1], f[3], h);
+            if (live[qq]) a.out[qg[qq] * a.G + g] = res;
+        }
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 static ConstBank g_bank;  // residency of one image per device in c_tt (pcb_cbank.cuh)
 
 void ttc_forget(const TTPlan *pl) {
     for (const auto &kv : pl->images) g_bank.forget(pl->dev, kv.second.id);
+    for (const auto &kv : pl->gimages) g_bank.forget(pl->dev, kv.second.id);
 }
 
 // The image holding forward cores `need_fwd` and transposed cores `need_T` (bit k = core k), or
@@ -416,6 +652,207 @@ int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_p
     *fits = true;
     for (int t = 0; t < prog.n_slots; ++t)
         if (int rc = ttc_launch_shared_one(pl, imgs[t], sub[t], d_points, N, d_out, st)) return rc;
+    return PCB_OK;
+}
+
+// ---- per-core launches (large trains) -----------------------------------------------------------------
+constexpr int64_t TTG_TILE = 1 << 21;  // queries per pass over the cores (bounds the state scratch)
+// step kernel: two 256-thread CTAs per SM, so that one CTA's state load / store phases overlap the
+// other's arithmetic (one 512-thread CTA: 2.94e8 values/s on the 10-D rank-20 train)
+constexpr int TTG_THREADS_STEP = 256, TTG_THREADS_COEFF = 256, TTG_QPT = 2;
+
+// chunk-major image of core k (orientation 0: forward [i][j][l]; 1: transposed [l][j][i])
+static const TTPlan::ConstImage *ttg_image(TTPlan *pl, int k, int orient) {
+    std::lock_guard<std::mutex> lock(pl->image_mutex);
+    const int key = 2 * k + orient;
+    auto it = pl->gimages.find(key);
+    if (it != pl->gimages.end()) return &it->second;
+    TTPlan::ConstImage &img = pl->gimages[key];
+    const TTParams &P = pl->P;
+    const int rows = orient ? P.r[k + 1] : P.r[k], cols = orient ? P.r[k] : P.r[k + 1], n = P.n[k];
+    const double *src = (orient ? pl->h_T.data() : pl->h_fwd.data()) + pl->core_off[k];  // [rows][n][cols]
+    const int nchunks = (cols + 15) / 16;
+    img.id = next_plan_id();
+    img.data.resize((size_t)rows * n * cols);
+    int l0 = 0;
+    size_t pos = 0;
+    for (int c = 0; c < TTG_MAX_CHUNKS; ++c) img.coff[c] = img.coffT[c] = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int w = cols / nchunks + (c < cols % nchunks ? 1 : 0);  // balanced widths, all <= 16
+        img.coff[c] = (int)pos;
+        img.coffT[c] = w;
+        for (int i = 0; i < rows; ++i)
+            for (int j = 0; j < n; ++j)
+                for (int l = 0; l < w; ++l)
+                    img.data[pos++] = src[((size_t)i * n + j) * cols + l0 + l];
+        l0 += w;
+    }
+    img.coff[TTG_MAX_CHUNKS] = nchunks;
+    // page-lock the image: an upload from pageable memory synchronises the stream first, which
+    // would drain the GPU between the per-core launches
+    cudaHostRegister(img.data.data(), img.data.size() * sizeof(double), cudaHostRegisterDefault);
+    cudaGetLastError();  // registration is an optimisation only
+    return &img;
+}
+
+template <typename K, typename A>
+static int ttg_launch(K kernel, TTPlan *pl, const TTPlan::ConstImage *img, const A &args, int threads,
+                      size_t smem, int64_t tile_n, const double *d_points, int64_t N, cudaStream_t st) {
+    if (smem > (size_t)pl->smem_optin)
+        return fail(PCB_EUNSUPPORTED, "TT per-core kernel needs %zu B of shared memory", smem);
+    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t cta = (int64_t)threads * TTG_QPT;
+    const int64_t blocks = (tile_n + cta - 1) / cta;
+    if (int rc = g_bank.acquire(pl->dev, img->id, st, [&](cudaStream_t s) {
+            return cudaMemcpyToSymbolAsync(c_tt, img->data.data(), img->data.size() * sizeof(double), 0,
+                                           cudaMemcpyHostToDevice, s);
+        }))
+        return rc;
+    kernel<<<(int)blocks, threads, smem, st>>>(args, d_points, N);
+    const cudaError_t e = cudaGetLastError();
+    g_bank.release(pl->dev, st);
+    g_launches.fetch_add(1);
+    if (e != cudaSuccess) return fail(PCB_ECUDA, "TT kernel launch failed: %s", cudaGetErrorString(e));
+    return PCB_OK;
+}
+
+// one core applied to the chain state: forward core k (left sweep) or transposed core k (right sweep)
+static int ttg_step(TTPlan *pl, int k, int orient, const double *s_in, double *s_out, int64_t pstride,
+                    int64_t q_begin, int64_t tile_n, const double *d_points, int64_t N, cudaStream_t st) {
+    const TTParams &P = pl->P;
+    const TTPlan::ConstImage *img = ttg_image(pl, k, orient);
+    TTGStep a;
+    a.r_in = orient ? P.r[k + 1] : P.r[k];
+    a.r_out = orient ? P.r[k] : P.r[k + 1];
+    a.n = P.n[k];
+    a.col = P.perm[k];
+    a.D = P.D;
+    a.lo = P.lo[k];
+    a.hi = P.hi[k];
+    a.nchunks = img->coff[TTG_MAX_CHUNKS];
+    for (int c = 0; c < TTG_MAX_CHUNKS; ++c) {
+        a.cbase[c] = img->coff[c];
+        a.cw[c] = img->coffT[c];
+    }
+    a.s_in = a.r_in == 1 ? nullptr : s_in;
+    a.s_out = s_out;
+    a.pstride = pstride;
+    a.q_begin = q_begin;
+    const size_t smem = (size_t)a.r_in * TTG_QPT * TTG_THREADS_STEP * sizeof(double);
+    return ttg_launch(ttc_gstep_kernel<TTG_QPT, TTG_THREADS_STEP>, pl, img, a, TTG_THREADS_STEP, smem,
+                      tile_n, d_points, N, st);
+}
+
+struct TTGScratch {  // stream-ordered scratch for the chain states of one tile
+    double *p = nullptr;
+    cudaStream_t st;
+    TTGScratch(int dev, size_t doubles, cudaStream_t s) : st(s) {
+        // keep freed scratch in the device's default pool (the default threshold 0 hands it back
+        // to the driver at every synchronisation, i.e. a fresh allocation per call)
+        static std::mutex m;
+        static bool tuned[ConstBank::MAX_DEV] = {false};
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (dev >= 0 && dev < ConstBank::MAX_DEV && !tuned[dev]) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                    uint64_t keep = UINT64_MAX;
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                }
+                tuned[dev] = true;
+            }
+        }
+        if (cudaMallocAsync(&p, doubles * sizeof(double), s) != cudaSuccess) p = nullptr;
+    }
+    ~TTGScratch() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+
+static int ttg_rmax(const TTPlan *pl) {
+    int rmax = 1;
+    for (int k = 0; k <= pl->P.D; ++k) rmax = std::max(rmax, pl->P.r[k]);
+    return rmax;
+}
+
+int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+    const TTParams &P = pl->P;
+    const int64_t tile = std::min<int64_t>(TTG_TILE, (N + 1023) / 1024 * 1024);
+    const int rmax = ttg_rmax(pl);
+    TTGScratch scratch(pl->dev, (size_t)2 * tile * rmax, st);
+    if (!scratch.p) return fail(PCB_ENOMEM, "cannot allocate %zu B of TT chain state", (size_t)16 * tile * rmax);
+    double *buf[2] = {scratch.p, scratch.p + (size_t)tile * rmax};
+    for (int64_t q0 = 0; q0 < N; q0 += tile) {
+        const int64_t tn = std::min(tile, N - q0);
+        int cur = 0;
+        for (int k = 0; k < P.D; ++k) {
+            double *dst = k == P.D - 1 ? d_out + q0 : buf[cur ^ 1];
+            if (int rc = ttg_step(pl, k, 0, buf[cur], dst, tile, q0, tn, d_points, N, st)) return rc;
+            cur ^= 1;
+        }
+    }
+    return PCB_OK;
+}
+
+int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
+                      double *d_out, cudaStream_t st) {
+    const TTParams &P = pl->P;
+    const int D = P.D;
+    const int64_t tile = std::min<int64_t>(TTG_TILE, (N + 1023) / 1024 * 1024);
+    const int rmax = ttg_rmax(pl);
+    TTGScratch scratch(pl->dev, (size_t)4 * tile * rmax, st);
+    if (!scratch.p) return fail(PCB_ENOMEM, "cannot allocate %zu B of TT chain state", (size_t)32 * tile * rmax);
+    double *L[2] = {scratch.p, scratch.p + (size_t)tile * rmax};
+    double *R[2] = {L[1] + (size_t)tile * rmax, L[1] + (size_t)2 * tile * rmax};
+    for (int64_t q0 = 0; q0 < N; q0 += tile) {
+        const int64_t tn = std::min(tile, N - q0);
+        int lcur = 0, lpos = 0;  // L[lcur] = left product over storage dims [0, lpos)
+        for (int t = 0; t < prog.n_slots; ++t) {
+            const int a = prog.slot_dim[t];
+            int rcur = 0;
+            for (int k = D - 1; k > a; --k) {  // right sweep on transposed cores
+                if (int rc = ttg_step(pl, k, 1, R[rcur], R[rcur ^ 1], tile, q0, tn, d_points, N, st)) return rc;
+                rcur ^= 1;
+            }
+            for (int k = lpos; k < a; ++k) {  // left sweep continues
+                if (int rc = ttg_step(pl, k, 0, L[lcur], L[lcur ^ 1], tile, q0, tn, d_points, N, st)) return rc;
+                lcur ^= 1;
+            }
+            lpos = a;
+            // coefficient pass on core a, register-accumulated index = the wider rank
+            const int orient = P.r[a + 1] >= P.r[a] ? 0 : 1;
+            const TTPlan::ConstImage *img = ttg_image(pl, a, orient);
+            TTGCoeff c;
+            c.r_rows = orient ? P.r[a + 1] : P.r[a];
+            c.r_acc = orient ? P.r[a] : P.r[a + 1];
+            c.n = P.n[a];
+            c.col = P.perm[a];
+            c.D = D;
+            c.G = prog.G;
+            c.lo = P.lo[a];
+            c.hi = P.hi[a];
+            c.nchunks = img->coff[TTG_MAX_CHUNKS];
+            for (int i = 0; i < TTG_MAX_CHUNKS; ++i) {
+                c.cbase[i] = img->coff[i];
+                c.cw[i] = img->coffT[i];
+            }
+            const double *vl = a == 0 ? nullptr : L[lcur], *vr = a == D - 1 ? nullptr : R[rcur];
+            c.s_rows = orient ? vr : vl;
+            c.s_acc = orient ? vl : vr;
+            c.pstride = tile;
+            c.q_begin = q0;
+            for (int g = 0; g < prog.G; ++g) {
+                const int rs = prog.row_slot[g];
+                c.row_kind[g] = rs == t ? prog.row_ord[g] : ((rs < 0 && t == 0) ? -1 : 0);
+            }
+            c.out = d_out;
+            const size_t smem =
+                (size_t)(c.r_rows + c.r_acc + c.n) * TTG_QPT * TTG_THREADS_COEFF * sizeof(double);
+            if (int rc = ttg_launch(ttc_gcoeff_kernel<TTG_QPT, TTG_THREADS_COEFF>, pl, img, c,
+                                    TTG_THREADS_COEFF, smem, tn, d_points, N, st))
+                return rc;
+        }
+    }
     return PCB_OK;
 }
 

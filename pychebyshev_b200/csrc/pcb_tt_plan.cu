@@ -106,6 +106,10 @@ static bool tt_build_shared_program(const TTFdProgram &prog, TTSharedProgram *sp
 
 TTPlan::~TTPlan() {
     ttc_forget(this);
+    for (auto &kv : gimages) {
+        cudaHostUnregister(kv.second.data.data());
+        cudaGetLastError();
+    }
     if (d_cores) cudaFree(d_cores);
 }
 
@@ -213,6 +217,22 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
             pl->const_threads_shared = t;
         }
         pl->last_fd_const = pl->const_shared_ok;
+        // large trains: every single core fits in the bank -> one launch per core
+        bool each_fits = env_int("PCB_TT_CONST", 1) != 0 && env_int("PCB_TT_GSTREAM", 1) != 0 && rmax <= 64;
+        for (int k = 0; k < D; ++k)
+            if (ranks[k] * n[k] * ranks[k + 1] > TT_CONST_MAX || n[k] > 64) each_fits = false;
+        pl->gstream_ok = each_fits && !pl->const_value_ok;
+        if (pl->gstream_ok && !pl->const_enabled) {  // host copies of the cores (ranks > 16)
+            pl->h_fwd.assign(cores_cat, cores_cat + fwd);
+            pl->h_T.resize((size_t)fwd);
+            size_t s2 = 0;
+            for (int k = 0; k < D; ++k)
+                for (int i = 0; i < ranks[k]; ++i)
+                    for (int j = 0; j < n[k]; ++j)
+                        for (int l = 0; l < ranks[k + 1]; ++l)
+                            pl->h_T[(size_t)pl->core_off[k] + ((size_t)l * n[k] + j) * ranks[k] + i] =
+                                cores_cat[s2++];
+        }
     }
     if (int rc = tt_pick_cfg(pl, false, &pl->cfg_chain)) {
         delete pl;
@@ -245,6 +265,8 @@ extern "C" PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N
     if (N == 0) return PCB_OK;
     PCB_REQUIRE(d_points && d_out, "null device pointer");
     DeviceGuard guard(pl->dev);
+    if (pl->gstream_ok)
+        return ttg_launch_value(pl, d_points, N, d_out, static_cast<cudaStream_t>(stream));
     if (pl->const_value_ok) {
         bool fits = false;
         const int rc = ttc_launch_value(pl, d_points, N, d_out, static_cast<cudaStream_t>(stream), &fits);
@@ -302,6 +324,10 @@ extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_
             const int rc = ttc_launch_shared(pl, sp, d_points, N, d_out, st, &fits);
             pl->last_fd_const = fits;
             if (rc || fits) return rc;
+        }
+        if (pl->gstream_ok) {
+            pl->last_fd_const = true;
+            return ttg_launch_shared(pl, sp, d_points, N, d_out, st);
         }
         return tt_launch_shared(pl, sp, d_points, N, d_out, st);
     }

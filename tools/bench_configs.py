@@ -118,7 +118,7 @@ def main():
         g = G.load(name)
         cores, domain, order = G.tt_parts(g)
         tt = pcb.ChebyshevTT.from_cores(cores, domain, order)
-        n = 20_000_000 if name == "tt_basket10d" else 5_000_000
+        n = 20_000_000 if name == "tt_basket10d" else 8_388_608
         pts = rand_points(domain, n)
         o1 = torch.empty((n, 1), dtype=torch.float64, device="cuda")
         ms = timeit(lambda: tt._plan().eval_device(pts, o1), reps=3)
