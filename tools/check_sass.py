@@ -18,11 +18,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pychebyshev_b200", "libpcb_b200.so")
 
-PATTERNS = ("ttc_value_kernel", "ttc_fd_shared_kernel", "spline_bank_kernel", "slider_bank_kernel")
+PATTERNS = ("ttc_value_kernel", "ttc_fd_shared_kernel", "ttc_gstep_kernel", "ttc_gcoeff_kernel",
+            "spline_bank_kernel", "slider_bank_kernel")
 
 
 def demangle_short(name):
-    m = re.search(r"(ttc_value_kernel|ttc_fd_shared_kernel|spline_bank_kernel|slider_bank_kernel)I(.*?)EEv", name)
+    m = re.search(r"(" + "|".join(PATTERNS) + r")I(.*?)EEv", name)
     if not m:
         return name
     args = re.findall(r"Li(\d+)E", m.group(2))
