@@ -113,6 +113,48 @@ def test_tt_oracle_fresh_seed_large_batch():
     scale_close(tt.eval_batch(pts), O.tt_eval_batch(cores, domain, dim_order, pts), "fresh batch")
 
 
+@pytest.mark.parametrize("rank,n_nodes,D", [(28, 10, 4), (33, 7, 5), (17, 16, 3)])
+def test_tt_large_rank_per_core_path(rank, n_nodes, D, monkeypatch):
+    """Trains whose cores fit the constant bank only one at a time: one launch per core, chain state
+    in global memory, output columns in 2-3 register chunks.  Checked against the oracle, against the
+    shared-memory kernels (PCB_TT_GSTREAM=0), over several tiles and with a ragged tail."""
+    import pychebyshev_b200 as pcb
+
+    rng = np.random.default_rng(rank)
+    ranks = [1] + [rank] * (D - 1) + [1]
+    ranks[1] = min(rank, 9)  # uneven ranks: the coefficient pass runs in both orientations
+    cores = [rng.standard_normal((ranks[k], n_nodes, ranks[k + 1])) / np.sqrt(ranks[k] * n_nodes)
+             for k in range(D)]
+    domain = [[-1.0 + 0.1 * k, 2.0 + 0.3 * k] for k in range(D)]
+    dim_order = list(range(D))[::-1]
+    # `domain` is in storage order; user column u is storage dim dim_order.index(u)
+    udom = np.array([domain[dim_order.index(u)] for u in range(D)])
+    n = (1 << 21) + 1000 + 37  # two tiles of the per-core executor + a ragged tail
+    pts = rng.uniform(udom[:, 0], udom[:, 1], size=(n, D))
+    orders = [[0] * D, [1] + [0] * (D - 1), [0] * (D - 1) + [2], [0] * D]
+    tt = pcb.ChebyshevTT.from_cores(cores, domain, dim_order)
+    info = tt._plan().info()
+    assert info["uniform_path_values"] == 0  # too large for the single-launch bank kernels
+    vals = tt.eval_batch(pts)
+    greeks = tt.eval_multi_batch(pts, orders)
+    monkeypatch.setenv("PCB_TT_GSTREAM", "0")
+    tt2 = pcb.ChebyshevTT.from_cores(cores, domain, dim_order)
+    vals2 = tt2.eval_batch(pts)
+    greeks2 = tt2.eval_multi_batch(pts, orders)
+    scale = float(np.max(np.abs(vals2)))
+    assert np.max(np.abs(vals - vals2)) <= 1e-12 * scale + 1e-14
+    assert np.array_equal(greeks[:, 0], greeks[:, 3])
+    for r, o in enumerate(orders):
+        tol = 1e-12 * scale + 1e-14  # propagated through the stencil (SURVEY.md 8(c))
+        for u, k in enumerate(o):
+            h = (udom[u, 1] - udom[u, 0]) * 1e-4
+            tol *= 1.0 if k == 0 else (1.0 / h if k == 1 else 4.0 / (h * h))
+        assert np.max(np.abs(greeks[:, r] - greeks2[:, r])) <= tol, (r, o)
+    sub = np.r_[0:700, (1 << 21) - 350:(1 << 21) + 350, n - 700:n]
+    ref = O.tt_eval_batch(cores, domain, dim_order, pts[sub])
+    scale_close(vals[sub], ref, f"rank {rank} per-core values")
+
+
 def test_tt_empty_and_single_row():
     g, tt = _tt("tt_4d")
     assert tt.eval_batch(np.zeros((0, 4))).shape == (0,)
