@@ -544,3 +544,26 @@ def test_native_pcb_loader_matches_reference(tmp_path):
     native = pcb.load_plan(path).eval(g["points"])[:, 0]
     scale_close(native, g["values"][:, 0], "native loader full_4d",
                 factor=G.extrapolation_factor(cheb.domain, cheb.nodes, cheb.weights, g["points"]))
+
+
+def test_c_host_evaluates_pcb_file_like_the_python_host(tmp_path):
+    """examples/pcb_eval.c (no Python, no torch): .pcb file -> pcb_plan_from_file -> pcb_plan_eval."""
+    import subprocess
+
+    from test_pcb_format import _build_c_host
+
+    exe = _build_c_host(tmp_path)
+    g, sp = _spline("spline_bs2d")
+    path = tmp_path / "spline.pcb"
+    sp.save(path)
+    rng = np.random.default_rng(8)
+    dom = np.asarray(g["domain"], dtype=np.float64)
+    pts = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.random((10_001, 2))
+    (tmp_path / "pts.f64").write_bytes(np.ascontiguousarray(pts).tobytes())
+    res = subprocess.run([exe, str(path), str(tmp_path / "pts.f64"), str(tmp_path / "out.f64")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "ChebyshevSpline, 2 dims, 10001 points" in res.stdout
+    got = np.frombuffer((tmp_path / "out.f64").read_bytes(), dtype=np.float64)
+    want = sp.eval_batch(pts, [0, 0])
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)) + 1e-14

@@ -172,3 +172,41 @@ def test_files_written_here_are_readable_by_the_reference_c_reader(tmp_path):
                              text=True, check=True).stdout
         got = float(out.strip().split()[-1])
         assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (got, want)
+
+
+def _build_c_host(tmp_path):
+    """gcc examples/pcb_eval.c against include/pcb_b200.h + libpcb_b200.so (+ libcudart)."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "pychebyshev_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA headers are not available")
+    exe = str(tmp_path / "pcb_eval")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(root, "examples", "pcb_eval.c"), "-L", libdir, "-lpcb_b200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", f"-Wl,-rpath,{libdir}",
+                    f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}", "-o", exe],
+                   check=True, capture_output=True)
+    return exe
+
+
+def test_c_host_compiles_against_the_header_and_reports_reference_errors(tmp_path):
+    """A plain C program is a client of the ABI: it builds from include/pcb_b200.h alone and gets
+    the reference's error text for a corrupt file (parsing precedes any CUDA call)."""
+    import subprocess
+
+    from pychebyshev_b200 import _lib
+
+    _lib.load()
+    exe = _build_c_host(tmp_path)
+    good = pcbfile.approx_bytes([[0.0, 1.0]], [2], np.array([1.0, 2.0]))
+    bad = tmp_path / "bad.pcb"
+    bad.write_bytes(b"XXXX" + good[4:])
+    (tmp_path / "pts.f64").write_bytes(np.zeros(4).tobytes())
+    res = subprocess.run([exe, str(bad), str(tmp_path / "pts.f64"), str(tmp_path / "out.f64")],
+                         capture_output=True, text=True)
+    assert res.returncode == 1 and "bad magic" in res.stderr
