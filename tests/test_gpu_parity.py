@@ -518,6 +518,99 @@ def test_tt_large_batch_properties():
     scale_close(fd[:, 0].cpu().numpy(), full[:1_000_000].cpu().numpy(), "fd value row", rel=1e-13)
 
 
+def test_spline_large_batch_properties():
+    """3e7 queries on device (C3 2-D spline): determinism, batch-position invariance, routing
+    consistency, linearity of the interpolation operator, exactness at the nodes."""
+    import torch
+
+    import pychebyshev_b200 as pcb
+
+    g, sp = _spline("spline_bs2d")
+    dom = np.asarray(g["domain"], dtype=np.float64)
+    n = 30_000_000
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    lo = torch.tensor(dom[:, 0], device="cuda")
+    hi = torch.tensor(dom[:, 1], device="cuda")
+    pts = lo + (hi - lo) * torch.rand((n, 2), generator=gen, device="cuda", dtype=torch.float64)
+    full = sp.eval_batch(pts, [0, 0])
+    assert torch.equal(full, sp.eval_batch(pts, [0, 0]))
+    perm = torch.randperm(n, generator=gen, device="cuda")
+    assert torch.equal(sp.eval_batch(pts[perm], [0, 0]), full[perm])
+    assert torch.equal(sp.eval_batch(pts[1_000_003:2_999_999], [0, 0]), full[1_000_003:2_999_999])
+    # routing: the piece index is the number of knots <= S (one knot at 100), whatever the batch
+    piece = sp.find_pieces(pts)
+    assert torch.equal(piece.to(torch.int64), (pts[:, 0] >= 100.0).to(torch.int64))
+    # linearity: spline(2 f - 3 g) = 2 spline(f) - 3 spline(g), g = another tensor on the same grid
+    knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+    n_nodes = [int(v) for v in g["piece_n_nodes"][0]]
+    rng = np.random.default_rng(4)
+    other = [rng.standard_normal(p[0].shape) for p in pieces]
+    dom_l = [list(map(float, r)) for r in g["domain"]]
+    sp_g = pcb.ChebyshevSpline.from_values(other, 2, dom_l, n_nodes, knots)
+    sp_c = pcb.ChebyshevSpline.from_values([2.0 * p[0] - 3.0 * o for p, o in zip(pieces, other)], 2, dom_l,
+                                           n_nodes, knots)
+    sub = pts[:5_000_000]
+    lhs = sp_c.eval_batch(sub, [0, 0])
+    rhs = 2.0 * full[:5_000_000] - 3.0 * sp_g.eval_batch(sub, [0, 0])
+    scale = float(torch.max(torch.abs(rhs)))
+    assert float(torch.max(torch.abs(lhs - rhs))) <= 1e-12 * scale + 1e-14
+    # exact at every node of every piece
+    for (t, nodes, w, dm) in pieces:
+        xs, ys = np.meshgrid(nodes[0], nodes[1], indexing="ij")
+        grid = np.column_stack([xs.ravel(), ys.ravel()])
+        inside = grid[:, 0] != 100.0  # the knot itself belongs to the right-hand piece
+        got = sp.eval_batch(grid, [0, 0])
+        assert np.array_equal(got[inside], t.ravel()[inside])
+    # spot check against the oracle
+    idx = torch.arange(0, n, n // 1500, device="cuda")
+    host = pts[idx].cpu().numpy()
+    ref = np.empty(len(host))
+    which = (host[:, 0] >= 100.0).astype(int)
+    for p, (t, nodes, w, dm) in enumerate(pieces):
+        m = which == p
+        ref[m] = O.full_eval_batch(t, nodes, w, dm, host[m], [0, 0])
+    scale_close(full[idx].cpu().numpy(), ref, "3e7 spline spot check")
+
+
+def test_full_tensor_core_path_properties():
+    """C1 (11^5) on the DMMA path, 1e6 queries: determinism, batch-position invariance, linearity in
+    the tensor, exactness at grid nodes."""
+    import torch
+
+    import pychebyshev_b200 as pcb
+    from pychebyshev_b200 import workloads as wl
+
+    g = G.load("full_bs5d")
+    nodes = G.split(g["nodes_cat"], [int(v) for v in g["n_nodes"]])
+    tensor = wl.grid_values(wl.bs_call_price, nodes)
+    rng = np.random.default_rng(9)
+    other = rng.standard_normal(tensor.shape)
+    mk = lambda t: pcb.ChebyshevApproximation.from_values(t, 5, wl.BS5D_DOMAIN, wl.BS5D_NODES)  # noqa: E731
+    a, b, c = mk(tensor), mk(other), mk(0.5 * tensor + 4.0 * other)
+    n = 1_000_000
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    lo = torch.tensor([d[0] for d in wl.BS5D_DOMAIN], device="cuda", dtype=torch.float64)
+    hi = torch.tensor([d[1] for d in wl.BS5D_DOMAIN], device="cuda", dtype=torch.float64)
+    pts = lo + (hi - lo) * torch.rand((n, 5), generator=gen, device="cuda", dtype=torch.float64)
+    zero = [[0, 0, 0, 0, 0]]
+    fa = a.eval_batch_multi(pts, zero, algo=2)
+    assert torch.equal(fa, a.eval_batch_multi(pts, zero, algo=2))
+    perm = torch.randperm(n, generator=gen, device="cuda")
+    assert torch.equal(a.eval_batch_multi(pts[perm], zero, algo=2), fa[perm])
+    fb = b.eval_batch_multi(pts, zero, algo=2)
+    fc = c.eval_batch_multi(pts, zero, algo=2)
+    rhs = 0.5 * fa + 4.0 * fb
+    assert float(torch.max(torch.abs(fc - rhs))) <= 1e-12 * float(torch.max(torch.abs(rhs))) + 1e-14
+    # grid nodes: the tensor entries themselves (one-hot weight rows), also on the tensor-core path
+    idx = rng.integers(0, 11, size=(4096, 5))
+    grid = np.column_stack([nodes[d][idx[:, d]] for d in range(5)])
+    got = a.eval_batch_multi(grid, zero, algo=2)[:, 0]
+    assert np.array_equal(got, tensor[tuple(idx.T)])
+    # the FMA evaluator agrees
+    f1 = a.eval_batch_multi(pts[:20_000], zero, algo=1)
+    scale_close(fa[:20_000].cpu().numpy(), f1.cpu().numpy(), "DMMA vs FMA evaluator")
+
+
 # ------------------------------------------------------------------------------------------
 # native .pcb loader (no Python grid arithmetic on the path)
 # ------------------------------------------------------------------------------------------
