@@ -390,10 +390,10 @@ struct BankContract {
             for (int d = LEVEL + 1; d < D; ++d) st *= g.n[d];
             const double *wnext = ws + (size_t)nl * wstride;
             for (int i = 0; i < nl; ++i) {
+                const double w = ws[i * wstride];  // issued before the row's dot product: latency hidden
                 double sub[GB];
                 BankContract<(LEVEL + 1 < D ? LEVEL + 1 : LEVEL), D, GB>::run(base + i * st, g, wnext,
                                                                              wstride, wl, sub);
-                const double w = ws[i * wstride];
 #pragma unroll
                 for (int j = 0; j < GB; ++j) out[j] = fma(w, sub[j], out[j]);
             }
