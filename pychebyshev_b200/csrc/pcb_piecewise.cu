@@ -40,11 +40,17 @@ struct SplinePlan : PlanBase {
     double *d_nodes = nullptr;   // all pieces: nodes then weights (same offsets)
     double *d_weights = nullptr;
     double *d_tensors = nullptr;  // per piece: [block][elem][GB]
-    // uniform-datapath path: all piece tensors + descriptors in this module's constant bank
+    // uniform-datapath path: all piece tensors + descriptors in this module's constant bank.  When
+    // the G outputs do not fit together they are split into parts of consecutive outputs, one
+    // launch (and one bank image) per part.
+    struct BankPart {
+        uint64_t id = 0;
+        int g0 = 0, G = 0, GB = 1;  // outputs [g0, g0 + G)
+        std::vector<double> h_bank;
+        std::vector<BankGrid> h_desc;
+    };
     bool bank_ok = false;
-    uint64_t plan_id = 0;
-    std::vector<double> h_bank;
-    std::vector<BankGrid> h_desc;
+    std::vector<BankPart> parts;
     size_t bank_smem = 0;
     ~SplinePlan() override;
     void free_all() {
@@ -425,7 +431,7 @@ __device__ __forceinline__ void bank_contract(const BankGrid &g, int b, const do
 
 template <int GB, int DM>
 __global__ void __launch_bounds__(BANK_THREADS)
-spline_bank_kernel(int D, int G, int P, const int *__restrict__ num_knots,
+spline_bank_kernel(int D, int G, int g0, int Gtot, int P, const int *__restrict__ num_knots,
                    const int *__restrict__ knot_off, const double *__restrict__ knots,
                    const double *__restrict__ pts, int64_t N, double *__restrict__ out,
                    int32_t *__restrict__ piece_out) {
@@ -461,7 +467,7 @@ spline_bank_kernel(int D, int G, int P, const int *__restrict__ num_knots,
     const int64_t q = q0 + s_perm[tid];
     const bool live = q < N;
     const double *x = pts + (live ? q : N - 1) * D;
-    double *o = out + (live ? q : N - 1) * G;
+    double *o = out + (live ? q : N - 1) * Gtot + g0;  // this launch writes outputs [g0, g0 + G)
     const unsigned present = __reduce_or_sync(0xffffffffu, 1u << mine);
     for (int p = 0; p < P; ++p) {
         if (!((present >> p) & 1u)) continue;  // uniform: REDUX leaves the mask in a uniform register
@@ -655,7 +661,7 @@ static int grid_launch_dims(const PlanBase *pl, const void *kernel, int threads,
 }
 
 SplinePlan::~SplinePlan() {
-    g_grid_bank.forget(dev, plan_id);
+    for (const BankPart &part : parts) g_grid_bank.forget(dev, part.id);
     free_all();
 }
 SliderPlan::~SliderPlan() {
@@ -729,10 +735,43 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
     for (int p = 0; p < P; ++p)
         grid_interleave(piece_tensors_host + (size_t)p * G, G, pl->GB, desc[p].size,
                         il.data() + desc[p].tensor_off);
-    pl->plan_id = next_plan_id();
-    // (pieces of different shapes are fine for the bank kernel; P <= 32 for its presence mask)
-    pl->bank_ok = bank_build(desc, il, tensor_total, piece_nodes_cat, piece_weights_cat, node_total,
-                             nullptr, nullptr, pl->smem_optin, &pl->h_bank, &pl->h_desc, &pl->bank_smem);
+    // Bank path (pieces of different shapes are fine; P <= 32 for the kernel's presence mask): all G
+    // outputs in one image if they fit, else parts of 4 / 2 / 1 consecutive outputs.
+    for (int per : {G, 4, 2, 1}) {
+        if (per > G || (per != G && per >= G)) continue;
+        std::vector<SplinePlan::BankPart> parts;
+        bool fits = true;
+        for (int g0 = 0; g0 < G && fits; g0 += per) {
+            SplinePlan::BankPart part;
+            part.g0 = g0;
+            part.G = std::min(per, G - g0);
+            part.GB = grid_pick_gb(part.G);
+            const int pblk = (part.G + part.GB - 1) / part.GB;
+            std::vector<GridDesc> pdesc(desc);
+            long long ptotal = 0;
+            for (int p = 0; p < P; ++p) {
+                pdesc[p].tensor_off = ptotal;
+                ptotal += pdesc[p].size * pblk * part.GB;
+            }
+            std::vector<double> pil((size_t)ptotal);
+            for (int p = 0; p < P; ++p)
+                grid_interleave(piece_tensors_host + (size_t)p * G + g0, part.G, part.GB, pdesc[p].size,
+                                pil.data() + pdesc[p].tensor_off);
+            size_t smem_part = 0;
+            fits = bank_build(pdesc, pil, ptotal, piece_nodes_cat, piece_weights_cat, node_total, nullptr,
+                              nullptr, pl->smem_optin, &part.h_bank, &part.h_desc, &smem_part);
+            if (fits) {
+                part.id = next_plan_id();
+                pl->bank_smem = std::max(pl->bank_smem, smem_part);
+                parts.push_back(std::move(part));
+            }
+        }
+        if (fits) {
+            pl->parts = std::move(parts);
+            pl->bank_ok = true;
+            break;
+        }
+    }
     DeviceGuard guard(dev);
     bool ok = guard.ok && upload(&pl->d_num_knots, meta.data(), meta.size()) &&
               upload(&pl->d_knots, knots_cat, (size_t)total_knots) &&
@@ -782,12 +821,17 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
     if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
     if (pl->bank_ok) {
-        const void *uk = BANK_KERNEL_TABLE(spline_bank_kernel, pl->GB, grid_pick_dm(pl->D));
-        void *uargs[] = {(void *)&pl->D, (void *)&pl->G, (void *)&pl->P, (void *)&pl->d_num_knots,
-                         (void *)&pl->d_knot_off, (void *)&pl->d_knots, (void *)&d_points, (void *)&N,
-                         (void *)&d_out, (void *)&d_piece};
-        return bank_launch(pl, pl->plan_id, pl->h_bank, pl->h_desc, uk, uargs, pl->bank_smem, N,
-                           static_cast<cudaStream_t>(stream));
+        for (const SplinePlan::BankPart &part : pl->parts) {
+            const void *uk = BANK_KERNEL_TABLE(spline_bank_kernel, part.GB, grid_pick_dm(pl->D));
+            int32_t *piece = part.g0 == 0 ? d_piece : nullptr;
+            void *uargs[] = {(void *)&pl->D, (void *)&part.G, (void *)&part.g0, (void *)&pl->G, (void *)&pl->P,
+                             (void *)&pl->d_num_knots, (void *)&pl->d_knot_off, (void *)&pl->d_knots,
+                             (void *)&d_points, (void *)&N, (void *)&d_out, (void *)&piece};
+            if (int rc = bank_launch(pl, part.id, part.h_bank, part.h_desc, uk, uargs, pl->bank_smem, N,
+                                     static_cast<cudaStream_t>(stream)))
+                return rc;
+        }
+        return PCB_OK;
     }
     const void *kernel = GRID_KERNEL_TABLE(spline_eval_kernel, pl->GB, grid_pick_dm(pl->D));
     int grid = 0;
