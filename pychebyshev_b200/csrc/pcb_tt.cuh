@@ -102,7 +102,7 @@ struct TTPlan : PlanBase {
     std::map<uint64_t, ConstImage> images;  // key: need_fwd mask | need_T mask << 32
     bool last_fd_const = false;
     // per-core launches with the chain state in global memory (large trains, pcb_tt_const.cu)
-    bool gstream_ok = false;
+    bool gstream_ok = false, gstream_fd_ok = false;  // values / price+Greeks (shared-memory limits)
     std::map<int, ConstImage> gimages;  // key 2 k + orientation; coff[c] chunk bases, coffT[c] widths
     const ConstImage *const_image(uint64_t need_fwd, uint64_t need_T);
     ~TTPlan() override;
@@ -135,7 +135,7 @@ int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_p
 // one launch per core, chain state in global memory (trains whose single cores fit in the bank)
 int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st);
 int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
-                      double *d_out, cudaStream_t st);
+                      double *d_out, cudaStream_t st, bool *fits);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

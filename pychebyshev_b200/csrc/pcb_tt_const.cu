@@ -795,9 +795,17 @@ int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_ou
 }
 
 int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
-                      double *d_out, cudaStream_t st) {
+                      double *d_out, cudaStream_t st, bool *fits) {
     const TTParams &P = pl->P;
     const int D = P.D;
+    // the coefficient pass of every differentiated dim keeps r_rows + r_acc + n rows in shared memory
+    *fits = true;
+    for (int t = 0; t < prog.n_slots; ++t) {
+        const int a = prog.slot_dim[t];
+        const size_t smem = (size_t)(P.r[a] + P.r[a + 1] + P.n[a]) * TTG_QPT * TTG_THREADS_COEFF * sizeof(double);
+        if (smem > (size_t)pl->smem_optin) *fits = false;
+    }
+    if (!*fits) return PCB_OK;  // caller falls back to the shared-memory kernels
     const int64_t tile = std::min<int64_t>(TTG_TILE, (N + 1023) / 1024 * 1024);
     const int rmax = ttg_rmax(pl);
     TTGScratch scratch(pl->dev, (size_t)4 * tile * rmax, st);

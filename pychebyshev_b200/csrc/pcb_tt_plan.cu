@@ -221,7 +221,16 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
         bool each_fits = env_int("PCB_TT_CONST", 1) != 0 && env_int("PCB_TT_GSTREAM", 1) != 0 && rmax <= 64;
         for (int k = 0; k < D; ++k)
             if (ranks[k] * n[k] * ranks[k + 1] > TT_CONST_MAX || n[k] > 64) each_fits = false;
-        pl->gstream_ok = each_fits && !pl->const_value_ok;
+        // shared-memory columns of the per-core kernels (256 threads x 2 query slots x 8 B per row):
+        // step: r_in rows; coefficient pass: r_rows + r_acc + n rows
+        size_t step_rows = 1, coeff_rows = 1;
+        for (int k = 0; k < D; ++k) {
+            step_rows = std::max<size_t>(step_rows, std::max(ranks[k], ranks[k + 1]));
+            coeff_rows = std::max<size_t>(coeff_rows, (size_t)ranks[k] + ranks[k + 1] + n[k]);
+        }
+        pl->gstream_ok = each_fits && !pl->const_value_ok && step_rows * 4096 <= (size_t)pl->smem_optin;
+        pl->gstream_fd_ok = pl->gstream_ok;  // per Greek set: ttg_launch_shared checks its own slots
+        (void)coeff_rows;
         if (pl->gstream_ok && !pl->const_enabled) {  // host copies of the cores (ranks > 16)
             pl->h_fwd.assign(cores_cat, cores_cat + fwd);
             pl->h_T.resize((size_t)fwd);
@@ -234,13 +243,21 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
                                 cores_cat[s2++];
         }
     }
+    // shared-memory kernel configurations; a train that only the per-core path can run keeps
+    // threads = 0 there (its launches then report the error instead of plan creation)
     if (int rc = tt_pick_cfg(pl, false, &pl->cfg_chain)) {
-        delete pl;
-        return rc;
+        if (!pl->gstream_ok) {
+            delete pl;
+            return rc;
+        }
+        pl->cfg_chain = TTCfg();
     }
     if (int rc = tt_pick_cfg(pl, true, &pl->cfg_shared)) {
-        delete pl;
-        return rc;
+        if (!pl->gstream_ok) {
+            delete pl;
+            return rc;
+        }
+        pl->cfg_shared = TTCfg();
     }
     DeviceGuard guard(dev);
     if (!guard.ok || cudaMalloc(&pl->d_cores, packed.size() * sizeof(double)) != cudaSuccess) {
@@ -325,9 +342,10 @@ extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_
             pl->last_fd_const = fits;
             if (rc || fits) return rc;
         }
-        if (pl->gstream_ok) {
-            pl->last_fd_const = true;
-            return ttg_launch_shared(pl, sp, d_points, N, d_out, st);
+        if (pl->gstream_fd_ok) {
+            const int rc = ttg_launch_shared(pl, sp, d_points, N, d_out, st, &fits);
+            pl->last_fd_const = fits;
+            if (rc || fits) return rc;
         }
         return tt_launch_shared(pl, sp, d_points, N, d_out, st);
     }
