@@ -47,6 +47,7 @@ struct DmmaParams {
 };
 
 struct FullPlan : PlanBase {
+    void *small = nullptr;  // one-piece spline plan on the constant bank (small tensors), or null
     GridDesc gd;
     int G = 0;
     double *d_nodes = nullptr;    // nodes then weights, dims concatenated
@@ -58,6 +59,7 @@ struct FullPlan : PlanBase {
     DmmaParams dm;
     size_t dm_smem = 0;
     ~FullPlan() override {
+        if (small) pcb_plan_destroy(small);
         if (d_nodes) cudaFree(d_nodes);
         if (d_tensors) cudaFree(d_tensors);
         if (d_prepared) cudaFree(d_prepared);
@@ -496,6 +498,18 @@ extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, co
         delete pl;
         return fail(PCB_ECUDA, "upload of the full-tensor plan failed");
     }
+    // small tensors: the constant-bank evaluator of pcb_piecewise.cu through a one-piece spline plan
+    // (no knots); kept only if that plan really runs from the bank
+    if (D <= 4 && gd.size * G <= 8192) {
+        std::vector<int32_t> no_knots(D, 0);
+        if (pcb_spline_plan_create(dev, D, no_knots.data(), nullptr, 1, n, nodes_cat, weights_cat, G,
+                                   tensors_host, &pl->small) != PCB_OK)
+            pl->small = nullptr;
+        else if (!spline_plan_uses_bank(pl->small)) {
+            pcb_plan_destroy(pl->small);
+            pl->small = nullptr;
+        }
+    }
     // tensor-core path: prepared copies in fragment order
     pl->dmma_ok = dmma_configure(pl, n);
     if (pl->dmma_ok) {
@@ -563,6 +577,7 @@ extern "C" PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t
                                 "budget of the tensor-core path", pl->gd.n[pl->gd.D - 1]);
         }
     }
+    if (algo == 0 && pl->small) return pcb_spline_eval(pl->small, d_points, N, d_out, nullptr, stream);
     const size_t smem = (size_t)pl->gd.sum_n * FULL_FMA_THREADS * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory",

@@ -46,6 +46,10 @@ inline void grid_interleave(const double *const *tensors, int G, int GB, long lo
 }
 inline int grid_pick_gb(int G) { return G >= 3 ? 4 : (G == 2 ? 2 : 1); }
 
+// Does this spline plan (pcb_piecewise.cu) run from the constant bank?  Used by the full-tensor plan,
+// which hands small tensors to a one-piece spline plan to get the uniform-datapath evaluator.
+bool spline_plan_uses_bank(const void *plan);
+
 #ifdef __CUDACC__
 
 // Normalised barycentric weight row of one dimension into row[i * stride], i < n (also used as

@@ -660,6 +660,11 @@ static int grid_launch_dims(const PlanBase *pl, const void *kernel, int threads,
     return PCB_OK;
 }
 
+bool spline_plan_uses_bank(const void *plan) {
+    const SplinePlan *pl = static_cast<const SplinePlan *>(plan);
+    return pl && pl->kind == PLAN_SPLINE && pl->bank_ok;
+}
+
 SplinePlan::~SplinePlan() {
     for (const BankPart &part : parts) g_grid_bank.forget(dev, part.id);
     free_all();

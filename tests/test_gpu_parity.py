@@ -199,6 +199,20 @@ def test_full_small_matches_reference(name, algo):
                     factor=fac)
 
 
+@pytest.mark.parametrize("name", FULL_SMALL)
+def test_full_small_auto_path_uses_bank_evaluator(name):
+    """algo 0 hands small tensors to the constant-bank evaluator (a one-piece spline plan): same
+    values as the reference and as the global-memory FMA evaluator, also for several outputs."""
+    g, cheb = _full(name)
+    fac = _full_factor(g, cheb)
+    orders = [list(map(int, o)) for o in g["orders"]]
+    auto = cheb.eval_batch_multi(g["points"], orders, algo=0)
+    fma = cheb.eval_batch_multi(g["points"], orders, algo=1)
+    for r, o in enumerate(orders):
+        scale_close(auto[:, r], g["values"][:, r], f"{name} auto order={o}", factor=fac)
+        scale_close(auto[:, r], fma[:, r], f"{name} auto vs fma order={o}", factor=fac)
+
+
 def test_full_per_order_api_matches_multi():
     g, cheb = _full("full_3d")
     multi = cheb.eval_batch_multi(g["points"], g["orders"])
