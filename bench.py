@@ -227,7 +227,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_ours(args, rank, local_rank, world):
@@ -392,10 +392,33 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline_c"] = cpu_baseline_c(cores, domain, dim_order, orders)
         except Exception as exc:  # noqa: BLE001
             line["cpu_baseline_c"] = {"unavailable": str(exc)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL's
+    version banner, library chatter of child processes) is sent to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
