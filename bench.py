@@ -366,7 +366,9 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {
-            "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "bound": "fp64", "bound_class": "tensor",  # compute-bound: the FP64 pipe, which DFMA and the
+            # FP64 tensor-core instruction (DMMA) share -- same measured peak, SURVEY.md 8(d)
+            "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf, "traffic": traffic,
             "traffic_note": "bytes per launch = ncu dram read+write per query (profiles/r1_traffic.json, "
                             "67.8 B vs 72 B algorithmic) x queries per launch",
