@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small, deterministic launch sequence of one kernel for ncu captures.
 
-usage: ncu_target.py {tt_value|tt_fd1|tt_fd2|full_dmma|full_fma|spline|spline_value|lookup} [N]
+usage: ncu_target.py {tt_value|tt_fd1|tt_fd2|full_dmma|full_fma|spline|spline_value|lookup|slider} [N]
 """
 import os
 import sys
@@ -52,6 +52,17 @@ def main():
         n = n or (148 * 256 if algo == 2 else 20000)
         pts = rand_points(wl.BS5D_DOMAIN, n)
         fn = lambda: cheb.eval_batch_multi(pts, wl.BS5D_GREEKS, algo=algo)  # noqa: E731
+    elif which == "slider":
+        from oracle import np_oracle as O
+
+        g = G.load("slider10d")
+        part, pivot_value, slides = G.slider_parts(g, O.diff_matrix)
+        dom = [list(map(float, r)) for r in g["domain"]]
+        sl = pcb.ChebyshevSlider.from_slides([s[0] for s in slides], 10, dom, [int(v) for v in g["n_nodes"]],
+                                             part, list(g["pivot_point"]), pivot_value)
+        n = n or 10_000_000
+        pts = rand_points(dom, n)
+        fn = lambda: sl.eval_batch(pts, [0] * 10)  # noqa: E731
     else:
         from oracle import np_oracle as O
 
