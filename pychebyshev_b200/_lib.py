@@ -66,7 +66,7 @@ class BackendUnavailable(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """Compile ``csrc/*.cu`` for sm_100a with nvcc into ``libpcb_b200.so`` (in-tree)."""
-    cmd = ["make", "-C", CSRC, "-j4"]
+    cmd = ["make", "-C", CSRC, f"-j{max(4, min(8, os.cpu_count() or 4))}"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc build failed:\n{res.stdout}\n{res.stderr}")
