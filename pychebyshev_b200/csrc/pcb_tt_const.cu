@@ -656,7 +656,8 @@ int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_p
 }
 
 // ---- per-core launches (large trains) -----------------------------------------------------------------
-constexpr int64_t TTG_TILE = 1 << 21;  // queries per pass over the cores (bounds the state scratch)
+constexpr int TTG_WAVES = 27;  // a tile = this many full waves of step CTAs (2 per SM x 512 queries):
+                               // ~4.1M queries on 148 SMs, no partial last wave, 2.6 GB of FD scratch at rank 20
 // step kernel: two 256-thread CTAs per SM, so that one CTA's state load / store phases overlap the
 // other's arithmetic (one 512-thread CTA: 2.94e8 values/s on the 10-D rank-20 train)
 constexpr int TTG_THREADS_STEP = 256, TTG_THREADS_COEFF = 256, TTG_QPT = 2;
@@ -777,7 +778,7 @@ static int ttg_rmax(const TTPlan *pl) {
 
 int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
     const TTParams &P = pl->P;
-    const int64_t tile = std::min<int64_t>(TTG_TILE, (N + 1023) / 1024 * 1024);
+    const int64_t tile = std::min<int64_t>((int64_t)TTG_WAVES * pl->sm_count * 1024, (N + 1023) / 1024 * 1024);
     const int rmax = ttg_rmax(pl);
     TTGScratch scratch(pl->dev, (size_t)2 * tile * rmax, st);
     if (!scratch.p) return fail(PCB_ENOMEM, "cannot allocate %zu B of TT chain state", (size_t)16 * tile * rmax);
@@ -806,7 +807,7 @@ int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_p
         if (smem > (size_t)pl->smem_optin) *fits = false;
     }
     if (!*fits) return PCB_OK;  // caller falls back to the shared-memory kernels
-    const int64_t tile = std::min<int64_t>(TTG_TILE, (N + 1023) / 1024 * 1024);
+    const int64_t tile = std::min<int64_t>((int64_t)TTG_WAVES * pl->sm_count * 1024, (N + 1023) / 1024 * 1024);
     const int rmax = ttg_rmax(pl);
     TTGScratch scratch(pl->dev, (size_t)4 * tile * rmax, st);
     if (!scratch.p) return fail(PCB_ENOMEM, "cannot allocate %zu B of TT chain state", (size_t)32 * tile * rmax);

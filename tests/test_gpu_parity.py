@@ -129,7 +129,8 @@ def test_tt_large_rank_per_core_path(rank, n_nodes, D, monkeypatch):
     dim_order = list(range(D))[::-1]
     # `domain` is in storage order; user column u is storage dim dim_order.index(u)
     udom = np.array([domain[dim_order.index(u)] for u in range(D)])
-    n = (1 << 21) + 1000 + 37  # two tiles of the per-core executor + a ragged tail
+    tile = 27 * 148 * 1024  # queries per pass of the per-core executor on a 148-SM B200
+    n = tile + 1000 + 37  # two tiles + a ragged tail
     pts = rng.uniform(udom[:, 0], udom[:, 1], size=(n, D))
     orders = [[0] * D, [1] + [0] * (D - 1), [0] * (D - 1) + [2], [0] * D]
     tt = pcb.ChebyshevTT.from_cores(cores, domain, dim_order)
@@ -150,7 +151,7 @@ def test_tt_large_rank_per_core_path(rank, n_nodes, D, monkeypatch):
             h = (udom[u, 1] - udom[u, 0]) * 1e-4
             tol *= 1.0 if k == 0 else (1.0 / h if k == 1 else 4.0 / (h * h))
         assert np.max(np.abs(greeks[:, r] - greeks2[:, r])) <= tol, (r, o)
-    sub = np.r_[0:700, (1 << 21) - 350:(1 << 21) + 350, n - 700:n]
+    sub = np.r_[0:700, tile - 350:tile + 350, n - 700:n]
     ref = O.tt_eval_batch(cores, domain, dim_order, pts[sub])
     scale_close(vals[sub], ref, f"rank {rank} per-core values")
 
