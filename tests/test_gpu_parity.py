@@ -675,3 +675,54 @@ def test_c_host_evaluates_pcb_file_like_the_python_host(tmp_path):
     got = np.frombuffer((tmp_path / "out.f64").read_bytes(), dtype=np.float64)
     want = sp.eval_batch(pts, [0, 0])
     assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)) + 1e-14
+
+
+def test_constant_bank_residency_across_plans_streams_and_threads():
+    """The constant bank holds one plan image at a time.  Plans that alternate on two streams,
+    driven from two host threads, must still see their own data: every result equals the serial one."""
+    import threading
+
+    import torch
+
+    g1, tt1 = _tt("tt_bs5d")
+    g2, tt2 = _tt("tt_4d")
+    g3, tt3 = _tt("tt_rank20_10d")  # per-core path: a new bank image at every launch
+    gs, sp = _spline("spline_bs2d")
+    cases = []
+    for g, obj in ((g1, tt1), (g2, tt2), (g3, tt3)):
+        cores, domain, dim_order = G.tt_parts(g)
+        D = len(domain)
+        udom = np.array([domain[dim_order.index(u)] for u in range(D)])
+        rng = np.random.default_rng(D)
+        pts = torch.from_numpy(rng.uniform(udom[:, 0], udom[:, 1], size=(150_001, D))).cuda()
+        plan = obj._plan()
+        cases.append((plan, pts, plan.eval_device(pts).clone()))
+        fd = obj._plan().with_orders(np.asarray(g["fd_orders"][:3]), 2)
+        cases.append((fd, pts, fd.eval_device(pts).clone()))
+    dom = np.asarray(gs["domain"], dtype=np.float64)
+    pts = torch.from_numpy(dom[:, 0] + (dom[:, 1] - dom[:, 0]) * np.random.default_rng(1).random((150_001, 2))).cuda()
+    plan = sp._plan([[0, 0]])
+    cases.append((plan, pts, plan.eval_device(pts).clone()))
+    torch.cuda.synchronize()
+
+    errors = []
+
+    def worker(offset):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for it in range(12):
+                    plan, pts, want = cases[(it + offset) % len(cases)]
+                    got = plan.eval_device(pts)
+                    if not torch.equal(got, want):
+                        errors.append((offset, it))
+            stream.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(k * 3,)) for k in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
