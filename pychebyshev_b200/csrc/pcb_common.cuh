@@ -49,6 +49,21 @@ int device_props(int dev, int *sm_count, int *smem_optin, int *cc);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Raise a kernel's dynamic shared-memory limit.  The attribute is per-function state shared by all
+// host threads, so it is always set to the same value (the device's opt-in maximum): a per-launch
+// value would race with a concurrent launch of the same kernel that needs more.
+template <typename K>
+inline cudaError_t allow_dynamic_smem(K kernel, size_t smem, int smem_optin) {
+    if (smem <= 48 * 1024) return cudaSuccess;  // within the default limit
+    cudaFuncAttributes attr;
+    const cudaError_t e = cudaFuncGetAttributes(&attr, reinterpret_cast<const void *>(kernel));
+    if (e != cudaSuccess) return e;
+    // the opt-in maximum covers static + dynamic shared memory
+    return cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_optin - (int)attr.sharedSizeBytes);
+}
+
 // RAII device switch: evaluation calls must not change the caller's current device.
 struct DeviceGuard {
     int prev = -1;

@@ -536,8 +536,7 @@ extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, co
 
 template <int KB>
 static int launch_dmma(FullPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
-    PCB_CUDA(cudaFuncSetAttribute(full_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->dm_smem));
+    PCB_CUDA(allow_dynamic_smem(full_dmma_kernel<KB>, pl->dm_smem, pl->smem_optin));
     const int64_t ntiles = (N + DM_QT - 1) / DM_QT;
     const int grid = (int)(ntiles < pl->sm_count ? ntiles : pl->sm_count);
     full_dmma_kernel<KB><<<grid, DM_THREADS, pl->dm_smem, st>>>(pl->dm, pl->d_nodes, pl->d_weights,
@@ -583,7 +582,7 @@ extern "C" PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory",
                     pl->gd.sum_n);
     const void *kernel = GRID_KERNEL_TABLE(full_fma_kernel, pl->GB, grid_pick_dm(pl->gd.D));
-    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
     int per_sm = 0;
     PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FULL_FMA_THREADS, smem));
     const int64_t want = (N + FULL_FMA_THREADS - 1) / FULL_FMA_THREADS;

@@ -623,7 +623,7 @@ static bool bank_build(const std::vector<GridDesc> &desc, const std::vector<doub
 static int bank_launch(const PlanBase *pl, uint64_t plan_id, const std::vector<double> &h_bank,
                        const std::vector<BankGrid> &h_desc, const void *kernel, void **args,
                        size_t smem, int64_t N, cudaStream_t st) {
-    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
     const int64_t blocks = (N + BANK_THREADS - 1) / BANK_THREADS;
     PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
     const int rc = g_grid_bank.acquire(pl->dev, plan_id, st, [&](cudaStream_t s) {
@@ -651,7 +651,7 @@ static bool upload(T **dptr, const T *src, size_t count) {
 
 static int grid_launch_dims(const PlanBase *pl, const void *kernel, int threads, size_t smem,
                             int64_t N, int *grid) {
-    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
     int per_sm = 0;
     PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     const int64_t want = (N + threads - 1) / threads;

@@ -348,7 +348,7 @@ __device__ __forceinline__ void tt_chain(const TTParams &P, const double *__rest
 template <typename K, typename... Args>
 static int tt_launch_kernel(K kernel, const TTPlan *pl, const TTCfg &cfg, int64_t N, cudaStream_t st,
                             Args... args) {
-    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    PCB_CUDA(allow_dynamic_smem(kernel, cfg.smem, pl->smem_optin));
     int per_sm = 0;
     PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, cfg.threads, cfg.smem));
     if (per_sm < 1)

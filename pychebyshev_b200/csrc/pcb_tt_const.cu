@@ -534,7 +534,7 @@ static int ttc_launch(K kernel, const TTPlan *pl, const TTPlan::ConstImage *img,
     const size_t smem = (size_t)nbuf * pl->P.rmaxp * qpt * threads * sizeof(double);
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "TT uniform-path kernel needs %zu B of shared memory", smem);
-    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
     const int64_t tile = (int64_t)threads * qpt;
     const int64_t ntiles = (N + tile - 1) / tile;
     if (ntiles > 0x7fffffffLL)
@@ -701,7 +701,7 @@ static int ttg_launch(K kernel, TTPlan *pl, const TTPlan::ConstImage *img, const
                       size_t smem, int64_t tile_n, const double *d_points, int64_t N, cudaStream_t st) {
     if (smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "TT per-core kernel needs %zu B of shared memory", smem);
-    PCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
     const int64_t cta = (int64_t)threads * TTG_QPT;
     const int64_t blocks = (tile_n + cta - 1) / cta;
     if (int rc = g_bank.acquire(pl->dev, img->id, st, [&](cudaStream_t s) {
