@@ -16,14 +16,16 @@ Two ways in:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 
 import numpy as np
 
 from . import _lib
 
-_CHUNK_BYTES = 64 << 20  # per-chunk input size of the host pipeline
-_NBUF = 3
+# host pipeline: per-chunk input size and ring depth (PCB_HOST_CHUNK_MB / PCB_HOST_NBUF override)
+_CHUNK_BYTES = int(os.environ.get("PCB_HOST_CHUNK_MB", "64")) << 20
+_NBUF = max(2, int(os.environ.get("PCB_HOST_NBUF", "3")))
 
 
 def _torch():
