@@ -113,7 +113,7 @@ def test_tt_oracle_fresh_seed_large_batch():
     scale_close(tt.eval_batch(pts), O.tt_eval_batch(cores, domain, dim_order, pts), "fresh batch")
 
 
-@pytest.mark.parametrize("rank,n_nodes,D", [(28, 10, 4), (33, 7, 5), (17, 16, 3)])
+@pytest.mark.parametrize("rank,n_nodes,D", [(28, 10, 4), (33, 7, 5), (17, 16, 3), (12, 11, 10)])
 def test_tt_large_rank_per_core_path(rank, n_nodes, D, monkeypatch):
     """Trains whose cores fit the constant bank only one at a time: one launch per core, chain state
     in global memory, output columns in 2-3 register chunks.  Checked against the oracle, against the
