@@ -72,7 +72,9 @@ PCB_API int pcb_tt_eval(void *plan, const double *d_points, int64_t N, double *d
  * rows (user frame, G x D int32, HOST pointer) -> d_out (N, G).  Orders > 2 -> PCB_EINVAL
  * ("Derivative order k not supported (use 1 or 2)").  `algo`: 0 = auto, 1 = one chain per stencil
  * point (any orders, <= 3 active dims per row), 2 = shared left/right partial products (rows with
- * <= 1 active dim). */
+ * <= 1 active dim).  One call takes at most 16 rows, each with at most 3 differentiated dims; the
+ * host layer (tt.py) splits larger row sets into several calls and unrolls deeper nested stencils
+ * into value launches, so every row set the reference's eval_multi accepts is served. */
 PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G, const int32_t *orders,
                    double *d_out, int algo, void *stream);
 
@@ -84,6 +86,12 @@ PCB_API int pcb_tt_plan_info(void *plan, int32_t *out8);
 
 /* Which algorithm pcb_tt_eval_fd(algo = 0) runs for these rows: 1 or 2; negative PCB_E* on error. */
 PCB_API int pcb_tt_fd_algo(void *plan, int G, const int32_t *orders);
+
+/* Which kernel family pcb_tt_eval_fd(algo) runs for these rows (reporting only -- evaluation keeps
+ * no state in the plan): 1 one chain per stencil point, 2 constant-bank shared-product kernel,
+ * 3 the same with one launch per differentiated dim, 4 one launch per core (large trains),
+ * 5 shared-memory shared-product kernel; negative PCB_E* on error. */
+PCB_API int pcb_tt_fd_path(void *plan, int G, const int32_t *orders, int algo);
 
 /* ---------------------------------------------------------------------------------------------
  * ChebyshevApproximation   (barycentric.py)
@@ -99,11 +107,44 @@ PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, const double 
                          const double *weights_cat, int G, const double *const *tensors_host,
                          void **plan);
 
+/* The same plan from the VALUE tensor alone: the tensor is uploaded once and
+ * the G derivative tensors are made ON THE DEVICE with the passes of _apply_derivative_passes
+ * (barycentric.py:982-989: for d = D-1..0, orders[g][d] times  T <- T x_d D_d^T), each output
+ * element one sequential FMA chain over k -- bit-identical to the reference's NumPy/OpenBLAS recipe
+ * on FMA-capable hosts.
+ *   diffmats_cat : .diff_matrices[d] (n_d x n_d, C-order) concatenated over d
+ *   values_host  : .tensor_values (C-order)
+ *   orders       : G x D derivative orders (HOST pointer) */
+PCB_API int pcb_full_plan_create_from_values(int dev, int D, const int32_t *n, const double *nodes_cat,
+                                     const double *weights_cat, const double *diffmats_cat,
+                                     const double *values_host, int G, const int32_t *orders,
+                                     void **plan);
+
 /* Replaces G calls of ChebyshevApproximation.vectorized_eval_batch (barycentric.py:992-1047),
  * one per pre-differentiated tensor: d_out (N, G).  `algo`: 0 = auto, 1 = thread-per-query FMA
  * evaluator, 2 = DMMA mode-1 GEMM with fused tail (D >= 3). */
 PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t N, double *d_out, int algo,
                   void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mode contractions of a C-order tensor in DEVICE memory
+ * ------------------------------------------------------------------------------------------ */
+
+/* One pass of _apply_derivative_passes (barycentric.py:982-989): d_dst = d_src x_axis D^T, same
+ * shape, out of place.  dmat_host: the n[axis] x n[axis] differentiation matrix (HOST, C-order). */
+PCB_API int pcb_tensor_deriv(int dev, int D, const int32_t *n, int axis, const double *dmat_host,
+                     const double *d_src, double *d_dst, void *stream);
+
+/* _slice_tensor (_extrude_slice.py:79-92): d_dst = tensordot(d_src, vec, axes=([axis],[0])); the
+ * axis is removed.  vec_host: n[axis] weights (HOST) -- the normalised barycentric weights of the
+ * slicing value, or a one-hot row on a node hit. */
+PCB_API int pcb_tensor_contract(int dev, int D, const int32_t *n, int axis, const double *vec_host,
+                        const double *d_src, double *d_dst, void *stream);
+
+/* _extrude_tensor (_extrude_slice.py:73-76): insert a new axis of length n_new at position `axis`
+ * of a D-dim tensor of shape n and replicate. */
+PCB_API int pcb_tensor_extrude(int dev, int D, const int32_t *n, int axis, int n_new, const double *d_src,
+                       double *d_dst, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ChebyshevSpline   (spline.py)
@@ -121,7 +162,9 @@ PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num_knots, con
                            const double *const *piece_tensors_host, void **plan);
 
 /* Replaces the routing lines of ChebyshevSpline.eval_batch (spline.py:677-690; single-point twin
- * _find_piece :414-445): d_piece[i] = C-order flat piece index, bit-exact integer work. */
+ * _find_piece :414-445): d_piece[i] = C-order flat piece index, bit-exact integer work.
+ * d_points needs only the natural 8-byte alignment; a 16-byte aligned base additionally enables
+ * 128-bit loads for 2-D splines. */
 PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int64_t N, int32_t *d_piece, void *stream);
 
 /* Replaces ChebyshevSpline.eval_batch (spline.py:633-700) for G derivative tensors: d_out (N, G).

@@ -78,9 +78,21 @@ class _HostPipe:
             return cls._pipes[dev]
 
     def _grow(self, bufs, b, numel, **kw):
+        """Grow-only buffer of ring slot ``b``.  Device buffers are allocated with the slot's OWN
+        stream current, so the caching allocator ties the block to the stream that uses it (a block
+        recycled from the caller's stream could otherwise be overwritten by the ring's H2D copy
+        while queued work of the caller still reads it)."""
         torch = _torch()
         if bufs[b] is None or bufs[b].numel() < numel:
-            bufs[b] = torch.empty(numel, dtype=torch.float64, **kw)
+            if "device" in kw:
+                with torch.cuda.stream(self.streams[b]):
+                    bufs[b] = None  # free the old block on its own stream first
+                    bufs[b] = torch.empty(numel, dtype=torch.float64, **kw)
+            else:
+                from . import _numa
+
+                with _numa.bound_to_device(self.dev):
+                    bufs[b] = torch.empty(numel, dtype=torch.float64, **kw)
         return bufs[b]
 
     def dev_in(self, b, numel):
@@ -96,12 +108,47 @@ class _HostPipe:
         return self._grow(self.h_out, b, numel, pin_memory=True)
 
 
-def pinned_empty(shape, dtype=np.float64):
-    """A NumPy array backed by pinned (page-locked) host memory; keeps its tensor alive."""
+def fingerprint(a: np.ndarray) -> tuple:
+    """Cheap identity + content token of a host array, used to invalidate cached device plans.
+
+    Rebinding is caught by the data pointer (the caches hold the arrays, so an address cannot be
+    reused while cached); in-place writes (``tensor_values[...] = ...``, ``core *= 2``) by a hash
+    of the content -- the whole array up to 8192 elements, otherwise ~4096 evenly strided samples
+    plus the last 8 elements (a write confined to unsampled elements of a large tensor is not
+    seen: call ``_reset_plans()`` / rebind after such surgery).
+    """
+    n = a.size
+    flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
+    if n <= 8192:
+        sample = flat
+    else:
+        sample = np.concatenate([flat[:: n // 4096], flat[-8:]])
+    return (a.__array_interface__["data"][0], a.shape, a.strides, hash(sample.tobytes()))
+
+
+def pinned_empty(shape, dtype=np.float64, device=None):
+    """A NumPy array backed by pinned (page-locked) host memory; keeps its tensor alive.
+
+    With ``device`` given the pages are first-touched by a thread bound to the CPUs of that GPU's
+    NUMA node (see :mod:`._numa`), so DMA to/from that GPU does not cross the socket interconnect.
+    """
     torch = _torch()
     tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
-    t = torch.empty(tuple(shape), dtype=tdtype, pin_memory=True)
+    from . import _numa
+
+    with _numa.bound_to_device(device):
+        t = torch.empty(tuple(shape), dtype=tdtype, pin_memory=True)
+        if device is not None and t.numel():
+            t.view(-1)[:: max(1, 4096 // t.element_size())] = 0  # first touch on this node
     return t.numpy()
+
+
+def host_pipeline_info(device=None) -> dict:
+    """Configuration of the host-buffer pipeline (reporting)."""
+    from . import _numa
+
+    return {"chunk_mb": _CHUNK_BYTES >> 20, "ring_depth": _NBUF,
+            "numa": _numa.describe(device)}
 
 
 class DevicePlan:
@@ -255,14 +302,29 @@ class TTPlan(DevicePlan):
         view.algo = algo
         return view
 
+    FD_PATHS = {1: "tt_fd_general_kernel (one chain per stencil point)",
+                2: "ttc_fd_shared_kernel (constant bank, one launch)",
+                3: "ttc_fd_shared_kernel (constant bank, one launch per differentiated dim)",
+                4: "ttc_gstep_kernel + ttc_gcoeff_kernel (one launch per core)",
+                5: "tt_fd_shared_kernel (shared memory)"}
+
     def info(self) -> dict:
-        """Which kernels evaluate this plan (reporting only)."""
+        """Which kernels evaluate this plan (reporting only; the plan keeps no per-call state)."""
         handle = self._handle if self._handle else self._owner._handle
+        lib = _lib.load()
         out = (C.c_int32 * 8)()
-        _lib.check(_lib.load().pcb_tt_plan_info(handle, out))
-        keys = ("uniform_path_values", "uniform_path_fd", "uniform_qpt", "uniform_threads_values",
+        _lib.check(lib.pcb_tt_plan_info(handle, out))
+        keys = ("uniform_path_values", "uniform_path_any_fd", "uniform_qpt", "uniform_threads_values",
                 "uniform_threads_fd", "smem_core_placement", "smem_fd_qpt", "smem_fd_threads")
-        return dict(zip(keys, [int(v) for v in out]))
+        info = dict(zip(keys, [int(v) for v in out]))
+        if self._orders is not None:
+            path = lib.pcb_tt_fd_path(handle, self.G, self._orders, self.algo)
+            if path < 0:
+                _lib.check(path)
+            info["fd_path"] = int(path)
+            info["fd_kernel"] = self.FD_PATHS.get(int(path), "?")
+            info["uniform_path_fd"] = int(path in (2, 3, 4))
+        return info
 
     def resolved_algo(self) -> int:
         """The algorithm ``pcb_tt_eval_fd`` runs for this view's rows (1 or 2)."""
@@ -307,6 +369,31 @@ class FullPlan(DevicePlan):
         super().__init__(handle, dev, D, len(keep))
         self.algo = algo
 
+    @classmethod
+    def from_values(cls, n_nodes, nodes, weights, diff_matrices, values, orders, device=None, algo=0):
+        """``pcb_full_plan_create_from_values``: upload the value tensor once; the derivative tensors
+        of ``orders`` are made on the device (bit-identical to the host recipe)."""
+        lib = _lib.load()
+        dev = require_device(device)
+        D = len(n_nodes)
+        _, n_p = _lib.as_i32(n_nodes)
+        _, nodes_p = _lib.as_f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in nodes]))
+        _, w_p = _lib.as_f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in weights]))
+        _, dm_p = _lib.as_f64(np.concatenate([np.ascontiguousarray(m, dtype=np.float64).ravel()
+                                              for m in diff_matrices]))
+        vals = np.ascontiguousarray(values, dtype=np.float64)
+        if vals.shape != tuple(n_nodes):
+            raise ValueError(f"tensor shape {vals.shape} does not match n_nodes {tuple(n_nodes)}")
+        ords = np.ascontiguousarray(np.asarray(orders, dtype=np.int32).reshape(-1, D))
+        handle = C.c_void_p()
+        _lib.check(lib.pcb_full_plan_create_from_values(
+            dev, D, n_p, nodes_p, w_p, dm_p, vals.ctypes.data_as(_lib._f64p), ords.shape[0],
+            ords.ctypes.data_as(_lib._i32p), C.byref(handle)))
+        self = object.__new__(cls)
+        DevicePlan.__init__(self, handle, dev, D, ords.shape[0])
+        self.algo = algo
+        return self
+
     def _launch(self, d_points, n, d_out, stream):
         _lib.check(_lib.load().pcb_full_eval(self._handle, d_points, n, d_out, self.algo, stream))
 
@@ -339,17 +426,35 @@ class SplinePlan(DevicePlan):
     def _launch(self, d_points, n, d_out, stream):
         _lib.check(_lib.load().pcb_spline_eval(self._handle, d_points, n, d_out, None, stream))
 
+    def lookup_device(self, points, out=None):
+        """Piece indices (int32) of a CUDA (N, D) float64 tensor, on the current stream."""
+        torch = _torch()
+        if (not isinstance(points, torch.Tensor) or not points.is_cuda
+                or points.dtype != torch.float64 or points.dim() != 2
+                or points.shape[1] != self.ndim):
+            raise ValueError(
+                f"points must be a CUDA float64 tensor of shape (N, {self.ndim}), got "
+                f"{tuple(getattr(points, 'shape', ()))} {getattr(points, 'dtype', type(points))}")
+        if points.device.index != self.dev:
+            raise ValueError(f"points live on {points.device}, plan on cuda:{self.dev}")
+        pts = points.contiguous()
+        n = pts.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=pts.device)
+        elif (out.dtype != torch.int32 or out.numel() != n or not out.is_contiguous()
+              or out.device != pts.device):
+            raise ValueError("out must be a contiguous int32 CUDA tensor with N elements")
+        stream = torch.cuda.current_stream(pts.device).cuda_stream
+        _lib.check(_lib.load().pcb_spline_lookup(self._handle, pts.data_ptr(), n, out.data_ptr(),
+                                                 stream))
+        return out
+
     def lookup(self, points):
         """Piece indices (int32) for device or host points."""
         torch = _torch()
         lib = _lib.load()
         if isinstance(points, torch.Tensor) and points.is_cuda:
-            pts = points.contiguous()
-            out = torch.empty(pts.shape[0], dtype=torch.int32, device=pts.device)
-            stream = torch.cuda.current_stream(pts.device).cuda_stream
-            _lib.check(lib.pcb_spline_lookup(self._handle, pts.data_ptr(), pts.shape[0],
-                                             out.data_ptr(), stream))
-            return out
+            return self.lookup_device(points)
         pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
         if pts.ndim != 2 or pts.shape[1] != self.ndim:
             raise ValueError(f"points must have shape (N, {self.ndim}), got {pts.shape}")

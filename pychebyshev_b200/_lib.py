@@ -39,8 +39,17 @@ SIGNATURES = {
                                  C.c_int, C.c_void_p]),
     "pcb_tt_plan_info": (C.c_int, [C.c_void_p, _i32p]),
     "pcb_tt_fd_algo": (C.c_int, [C.c_void_p, C.c_int, _i32p]),
+    "pcb_tt_fd_path": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int]),
     "pcb_full_plan_create": (C.c_int, [C.c_int, C.c_int, _i32p, _f64p, _f64p, C.c_int,
                                        C.POINTER(_f64p), _vpp]),
+    "pcb_full_plan_create_from_values": (C.c_int, [C.c_int, C.c_int, _i32p, _f64p, _f64p, _f64p, _f64p,
+                                                   C.c_int, _i32p, _vpp]),
+    "pcb_tensor_deriv": (C.c_int, [C.c_int, C.c_int, _i32p, C.c_int, _f64p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "pcb_tensor_contract": (C.c_int, [C.c_int, C.c_int, _i32p, C.c_int, _f64p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "pcb_tensor_extrude": (C.c_int, [C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "pcb_full_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "pcb_spline_plan_create": (C.c_int, [C.c_int, C.c_int, _i32p, _f64p, C.c_int, _i32p, _f64p, _f64p,
                                          C.c_int, C.POINTER(_f64p), _vpp]),

@@ -16,7 +16,7 @@ from typing import Callable, List, Sequence
 import numpy as np
 
 from . import _grid, pcbfile
-from ._engine import FullPlan
+from ._engine import FullPlan, fingerprint
 
 
 def _unwrap(value, attr):
@@ -233,12 +233,17 @@ class ChebyshevApproximation(_DerivativeIds):
         self._plan_tensor_id = None
         self._deriv_cache = {}
 
+    def _validate_caches(self):
+        """Drop cached plans / derivative tensors when ``tensor_values`` was rebound or edited."""
+        token = fingerprint(self.tensor_values)
+        if self._plan_tensor_id != token:
+            self._plans, self._deriv_cache = {}, {}
+            self._plan_tensor_id = token
+
     def derivative_tensor(self, order) -> np.ndarray:
         """Pre-differentiated tensor for one derivative multi-index (host, cached)."""
         key = tuple(int(o) for o in order)
-        if self._plan_tensor_id != id(self.tensor_values):
-            self._plans, self._deriv_cache = {}, {}
-            self._plan_tensor_id = id(self.tensor_values)
+        self._validate_caches()
         if key not in self._deriv_cache:
             self._deriv_cache[key] = _grid.differentiate_tensor(
                 self.tensor_values, self.diff_matrices, key)
@@ -248,7 +253,7 @@ class ChebyshevApproximation(_DerivativeIds):
         if self.tensor_values is None:
             raise RuntimeError("Call build() first")
         orders = _grid.normalize_orders(orders, self.num_dimensions)
-        tensors = [self.derivative_tensor(o) for o in orders]  # also validates the cache
+        self._validate_caches()
         from ._engine import require_device
 
         dev = require_device(self.device if device is None else device)
@@ -256,8 +261,115 @@ class ChebyshevApproximation(_DerivativeIds):
         if key not in self._plans:
             if len(self._plans) >= 8:  # bound device memory held by stale order sets
                 self._plans.pop(next(iter(self._plans)))
-            self._plans[key] = FullPlan(self.n_nodes, self.nodes, self.weights, tensors, dev, algo)
+            if os.environ.get("PCB_DEVICE_DERIV", "1") != "0" and max(self.n_nodes) <= 64:
+                # N3: one upload of the value tensor, derivative tensors made on the device
+                self._plans[key] = FullPlan.from_values(
+                    self.n_nodes, self.nodes, self.weights, self.diff_matrices, self.tensor_values,
+                    orders, dev, algo)
+            else:
+                tensors = [self.derivative_tensor(o) for o in orders]
+                self._plans[key] = FullPlan(self.n_nodes, self.nodes, self.weights, tensors, dev,
+                                            algo)
         return self._plans[key]
+
+    # ------------------------------------------------------------------ slice / extrude (N3)
+    def _derived(self, tensor, nodes, weights, diff_matrices, domain, n_nodes):
+        obj = object.__new__(ChebyshevApproximation)
+        obj.function = None
+        obj.num_dimensions = len(n_nodes)
+        obj.domain = domain
+        obj.n_nodes = n_nodes
+        obj.max_derivative_order = self.max_derivative_order
+        obj.error_threshold = None
+        obj.max_n = self.max_n
+        obj.special_points = None
+        obj.additional_data = None
+        obj.n_workers = None
+        obj.descriptor = ""
+        obj.device = self.device
+        obj.build_time = 0.0
+        obj.n_evaluations = 0
+        obj.nodes, obj.weights, obj.diff_matrices = nodes, weights, diff_matrices
+        obj.tensor_values = tensor
+        obj._init_derivative_ids()
+        obj._reset_plans()
+        return obj
+
+    def slice(self, params, *, device=None) -> "ChebyshevApproximation":
+        """Fix dimensions at given values (reference ``barycentric.py:2067-2154``); the mode
+        contractions run on the device (``device_tensor.slice_axis``)."""
+        if self.tensor_values is None:
+            raise RuntimeError("Call build() first")
+        from . import device_tensor as DT
+
+        ndim = self.num_dimensions
+        if isinstance(params, tuple) and len(params) == 2 and isinstance(params[0], (int, np.integer)):
+            params = [params]
+        params = [tuple(p) for p in params]
+        if len(params) >= ndim:
+            raise ValueError(f"Cannot slice all {ndim} dimensions (would produce 0D result)")
+        seen = set()
+        for dim_idx, value in params:
+            if not isinstance(dim_idx, (int, np.integer)):
+                raise TypeError(f"dim_index must be int, got {type(dim_idx).__name__}")
+            if dim_idx < 0 or dim_idx >= ndim:
+                raise ValueError(f"dim_index {dim_idx} out of range [0, {ndim - 1}]")
+            if dim_idx in seen:
+                raise ValueError(f"Duplicate dim_index {dim_idx}")
+            seen.add(dim_idx)
+            lo, hi = self.domain[dim_idx]
+            if value < lo or value > hi:
+                raise ValueError(
+                    f"Slice value {value} for dim {dim_idx} is outside domain [{lo}, {hi}]")
+        nodes, weights, dms = list(self.nodes), list(self.weights), list(self.diff_matrices)
+        domain = [list(b) for b in self.domain]
+        n_nodes = list(self.n_nodes)
+        t = DT.to_device(self.tensor_values, self.device if device is None else device)
+        for dim_idx, value in sorted(params, key=lambda p: p[0], reverse=True):
+            t = DT.slice_axis(t, dim_idx, nodes[dim_idx], weights[dim_idx], value)
+            for lst in (nodes, weights, dms, domain, n_nodes):
+                del lst[dim_idx]
+        return self._derived(t.cpu().numpy(), nodes, weights, dms, domain, n_nodes)
+
+    def extrude(self, params, *, device=None) -> "ChebyshevApproximation":
+        """Add dimensions along which the function is constant (reference
+        ``barycentric.py:1977-2065``); replication runs on the device."""
+        if self.tensor_values is None:
+            raise RuntimeError("Call build() first")
+        from . import device_tensor as DT
+
+        if isinstance(params, tuple) and len(params) == 3 and isinstance(params[0], (int, np.integer)):
+            params = [params]
+        params = [tuple(p) for p in params]
+        new_ndim = self.num_dimensions + len(params)
+        seen = set()
+        for dim_idx, bounds, n in params:
+            if not isinstance(dim_idx, (int, np.integer)):
+                raise TypeError(f"dim_index must be int, got {type(dim_idx).__name__}")
+            if dim_idx < 0 or dim_idx >= new_ndim:
+                raise ValueError(f"dim_index {dim_idx} out of range [0, {new_ndim - 1}]")
+            if dim_idx in seen:
+                raise ValueError(f"Duplicate dim_index {dim_idx}")
+            seen.add(dim_idx)
+            lo, hi = bounds
+            if lo >= hi:
+                raise ValueError(f"Domain bounds must satisfy lo < hi, got [{lo}, {hi}]")
+            if not isinstance(n, (int, np.integer)) or n < 2:
+                raise ValueError(f"n_nodes must be int >= 2, got {n}")
+        nodes, weights, dms = list(self.nodes), list(self.weights), list(self.diff_matrices)
+        domain = [list(b) for b in self.domain]
+        n_nodes = list(self.n_nodes)
+        t = DT.to_device(self.tensor_values, self.device if device is None else device)
+        for dim_idx, (lo, hi), n in sorted(params, key=lambda p: p[0]):
+            t = DT.extrude_axis(t, dim_idx, n)
+            x = _grid.cheb_nodes(float(lo), float(hi), int(n))
+            w = _grid.bary_weights(x)
+            nodes.insert(dim_idx, x)
+            weights.insert(dim_idx, w)
+            dms.insert(dim_idx, _grid.diff_matrix(x, w))
+            domain.insert(dim_idx, [lo, hi])
+            n_nodes.insert(dim_idx, int(n))
+        return self._derived(t.cpu().numpy(), nodes, weights, dms, domain, n_nodes)
 
     # ------------------------------------------------------------------ evaluation
     def eval_batch_multi(self, points, derivative_orders, *, out=None, device=None, algo=0):

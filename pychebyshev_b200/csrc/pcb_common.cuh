@@ -49,6 +49,11 @@ int device_props(int dev, int *sm_count, int *smem_optin, int *cc);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// pcb_tensor.cu: out[o, j, i] = sum_k src[o, k, i] * M[j * n + k] (sequential FMA chain over k),
+// src (outer, n, inner) -> dst (outer, rows, inner), everything in device memory
+int tensor_mode_launch(int dev, const double *d_src, double *d_dst, long long outer, int n,
+                       long long inner, int rows, const double *d_M, cudaStream_t st);
+
 // Raise a kernel's dynamic shared-memory limit.  The attribute is per-function state shared by all
 // host threads, so it is always set to the same value (the device's opt-in maximum): a per-launch
 // value would race with a concurrent launch of the same kernel that needs more.

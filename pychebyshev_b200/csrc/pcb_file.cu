@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <new>
+#include <stdexcept>
 
 #include "pcb_common.cuh"
 
@@ -66,24 +68,33 @@ static int parse_pcb(const char *path, PcbFile *out) {
             return fail(PCB_EINVAL, "domain[%u]: lo (%g) must be < hi (%g)", d, out->lo[d], out->hi[d]);
     std::vector<uint32_t> nn(D);
     if (!take(raw, pos, nn.data(), 4 * D)) return fail(PCB_EINVAL, "unexpected EOF reading uint32 array");
+    // every size below is bounded by the bytes that are actually left in the file before anything
+    // is allocated: a crafted header cannot request more memory than the file is long
+    const size_t max_doubles = (raw.size() - pos) / 8;
     size_t per = 1;
     for (uint32_t d = 0; d < D; ++d) {
         if (nn[d] < 1) return fail(PCB_EINVAL, "n_nodes[%u] must be >= 1, got %u", d, nn[d]);
+        if (nn[d] > 0x7fffffffu || per > max_doubles / nn[d])
+            return fail(PCB_EINVAL, "unexpected EOF reading f64 array (tensor of n_nodes[%u]=%u "
+                        "exceeds the %zu bytes left)", d, nn[d], raw.size() - pos);
         out->n[d] = (int32_t)nn[d];
         per *= nn[d];
-        if (per > ((size_t)1 << 34)) return fail(PCB_EINVAL, "tensor too large");
     }
     out->P = 1;
     out->num_knots.assign(D, 0);
     if (tag == 2) {
         std::vector<uint32_t> nk(D);
         if (!take(raw, pos, nk.data(), 4 * D)) return fail(PCB_EINVAL, "unexpected EOF reading uint32 array");
-        size_t total = 0;
-        long long expect = 1;
+        const size_t left = (raw.size() - pos) / 8;
+        size_t total = 0, expect = 1;
         for (uint32_t d = 0; d < D; ++d) {
+            if (nk[d] > left || total + nk[d] > left)
+                return fail(PCB_EINVAL, "unexpected EOF reading f64 array (num_knots[%u]=%u)", d, nk[d]);
             out->num_knots[d] = (int32_t)nk[d];
             total += nk[d];
-            expect *= (long long)nk[d] + 1;
+            if (expect > left / ((size_t)nk[d] + 1) + 1)  // more pieces than doubles in the file
+                return fail(PCB_EINVAL, "unexpected EOF reading f64 array (too many pieces)");
+            expect *= (size_t)nk[d] + 1;
         }
         out->knots.resize(total);
         if (total && !take(raw, pos, out->knots.data(), 8 * total))
@@ -97,14 +108,18 @@ static int parse_pcb(const char *path, PcbFile *out) {
         }
         uint32_t P;
         if (!take(raw, pos, &P, 4)) return fail(PCB_EINVAL, "unexpected EOF reading uint32");
-        if ((long long)P != expect)
-            return fail(PCB_EINVAL, "num_pieces=%u does not match prod(num_knots+1)=%lld", P, expect);
+        if ((size_t)P != expect)
+            return fail(PCB_EINVAL, "num_pieces=%u does not match prod(num_knots+1)=%zu", P, expect);
+        if (P > 0x7fffffffu) return fail(PCB_EINVAL, "num_pieces=%u too large", P);
         out->P = (int)P;
     }
-    out->values.resize(per * out->P);
-    if (!take(raw, pos, out->values.data(), 8 * per * out->P))
-        return fail(PCB_EINVAL, "unexpected EOF reading f64 array (wanted %zu bytes, got %zu)",
-                    8 * per * out->P, raw.size() - pos);
+    const size_t avail = (raw.size() - pos) / 8;
+    if (per > avail / (size_t)out->P)
+        return fail(PCB_EINVAL, "unexpected EOF reading f64 array (wanted %zu x %d doubles, %zu bytes left)",
+                    per, out->P, raw.size() - pos);
+    out->values.resize(per * (size_t)out->P);
+    if (!take(raw, pos, out->values.data(), 8 * per * (size_t)out->P))
+        return fail(PCB_EINVAL, "unexpected EOF reading f64 array");
     for (double v : out->values)
         if (!std::isfinite(v)) return fail(PCB_EINVAL, "tensor_values contains NaN or Inf");
     return PCB_OK;
@@ -131,7 +146,19 @@ static void make_weights(const double *x, int n, double *w) {
 using namespace pcb;
 
 // kind: 1 = ChebyshevApproximation, 2 = ChebyshevSpline
+static int plan_from_file(int dev, const char *path, void **plan, int *kind, int *D);
+
 extern "C" PCB_API int pcb_plan_from_file(int dev, const char *path, void **plan, int *kind, int *D) {
+    try {  // no C++ exception may cross the C ABI
+        return plan_from_file(dev, path, plan, kind, D);
+    } catch (const std::bad_alloc &) {
+        return fail(PCB_ENOMEM, "out of host memory while loading %s", path ? path : "(null)");
+    } catch (const std::exception &e) {
+        return fail(PCB_EINVAL, "loading %s failed: %s", path ? path : "(null)", e.what());
+    }
+}
+
+static int plan_from_file(int dev, const char *path, void **plan, int *kind, int *D) {
     PCB_REQUIRE(path && plan, "null argument");
     PcbFile pf;
     if (int rc = parse_pcb(path, &pf)) return rc;

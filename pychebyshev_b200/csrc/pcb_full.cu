@@ -362,25 +362,40 @@ full_dmma_kernel(const __grid_constant__ DmmaParams P, const double *__restrict_
 // host side
 // ---------------------------------------------------------------------------------------------
 
-// Reorder one C-order tensor into MMA B-fragment order:
+// Reorder one C-order tensor (device) into MMA B-fragment order (device):
 //   prepared[((lg * nc + c) * nd + d) * KB + kb][lane] = T[lead = 8 lg + lane/4][c][d][e = 4 kb + lane%4]
-static void dmma_prepare(const DmmaParams &P, const double *t, double *dst) {
+// One thread per output element: coalesced stores, gathered loads (each 32-lane group reads 8 rows
+// of 4 consecutive doubles).  Runs once per tensor at plan creation.
+__global__ void __launch_bounds__(256)
+dmma_prepare_kernel(const __grid_constant__ DmmaParams P, const double *__restrict__ t,
+                    double *__restrict__ dst) {
     const int nlast = P.n[P.D - 1];
     const long long s_d = nlast;
     const long long s_c = s_d * P.nd;
     const long long s_lead = s_c * P.nc;
-    size_t o = 0;
-    for (int lg = 0; lg < P.LG; ++lg)
-        for (int c = 0; c < P.nc; ++c)
-            for (int d = 0; d < P.nd; ++d)
-                for (int kb = 0; kb < P.KB; ++kb)
-                    for (int lane = 0; lane < 32; ++lane, ++o) {
-                        const int lead = lg * 8 + lane / 4;
-                        const int e = kb * 4 + lane % 4;
-                        dst[o] = (lead < P.L && e < nlast)
-                                     ? t[lead * s_lead + c * s_c + d * s_d + e]
-                                     : 0.0;
-                    }
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < P.gstride;
+         o += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(o & 31);
+        long long r = o >> 5;
+        const int kb = (int)(r % P.KB);
+        r /= P.KB;
+        const int d = (int)(r % P.nd);
+        r /= P.nd;
+        const int c = (int)(r % P.nc);
+        const long long lg = r / P.nc;
+        const long long lead = lg * 8 + lane / 4;
+        const int e = kb * 4 + lane % 4;
+        dst[o] = (lead < P.L && e < nlast) ? t[lead * s_lead + c * s_c + d * s_d + e] : 0.0;
+    }
+}
+
+// dst[e * GB + slot] = src[e]: one output of an interleaved block [elem][GB]
+__global__ void __launch_bounds__(256)
+interleave_kernel(const double *__restrict__ src, double *__restrict__ dst, long long size, int GB,
+                  int slot) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < size;
+         e += (long long)gridDim.x * blockDim.x)
+        dst[e * GB + slot] = src[e];
 }
 
 static bool dmma_configure(FullPlan *pl, const int32_t *n) {
@@ -447,12 +462,107 @@ static bool dmma_configure(FullPlan *pl, const int32_t *n) {
 
 using namespace pcb;
 
-extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, const double *nodes_cat,
-                                    const double *weights_cat, int G,
-                                    const double *const *tensors_host, void **plan) {
-    PCB_REQUIRE(plan && n && nodes_cat && weights_cat && tensors_host, "null argument");
-    PCB_REQUIRE(D >= 1 && D <= GRID_MAXD, "num_dimensions %d outside [1, %d]", D, GRID_MAXD);
-    PCB_REQUIRE(G >= 1 && G <= 64, "number of derivative tensors %d outside [1, 64]", G);
+namespace pcb {
+
+// Source of the G C-order tensors of a plan, as DEVICE pointers valid until the next call.
+struct TensorSource {
+    virtual const double *get(int g) = 0;   // nullptr + last error on failure
+    virtual const double *host(int g) { return nullptr; }  // host copy if there is one
+    virtual ~TensorSource() {}
+};
+
+// Tensors given on the host (made with the reference's NumPy recipe): staged through one buffer.
+struct HostTensorSource : TensorSource {
+    const double *const *tensors;
+    long long size;
+    double *d_stage = nullptr;
+    HostTensorSource(const double *const *t, long long sz) : tensors(t), size(sz) {}
+    const double *get(int g) override {
+        if (!d_stage && cudaMalloc(&d_stage, (size_t)size * sizeof(double)) != cudaSuccess) {
+            fail(PCB_ENOMEM, "cannot allocate the tensor staging buffer");
+            return nullptr;
+        }
+        if (cudaMemcpy(d_stage, tensors[g], (size_t)size * sizeof(double), cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+            fail(PCB_ECUDA, "upload of tensor %d failed", g);
+            return nullptr;
+        }
+        return d_stage;
+    }
+    const double *host(int g) override { return tensors[g]; }
+    ~HostTensorSource() override {
+        if (d_stage) cudaFree(d_stage);
+    }
+};
+
+// N3: the value tensor is uploaded ONCE and every derivative tensor is made on the device by the
+// passes of _apply_derivative_passes (barycentric.py:982-989: for d = D-1..0, order[d] times
+// T <- T x_d D_d^T), bit-identical to the host recipe (pcb_tensor.cu).
+struct DerivTensorSource : TensorSource {
+    int dev, D;
+    const int32_t *n;
+    const int32_t *orders;  // G x D
+    long long size;
+    double *d_val = nullptr, *d_buf[2] = {nullptr, nullptr}, *d_dm = nullptr;
+    std::vector<size_t> dm_off;
+    std::vector<double> h_copy;
+    bool ok = false;
+    DerivTensorSource(int dev_, int D_, const int32_t *n_, const double *dmats_cat, const double *values,
+                      const int32_t *orders_, long long sz)
+        : dev(dev_), D(D_), n(n_), orders(orders_), size(sz) {
+        size_t total = 0;
+        for (int d = 0; d < D; ++d) {
+            dm_off.push_back(total);
+            total += (size_t)n[d] * n[d];
+        }
+        const size_t tb = (size_t)size * sizeof(double);
+        ok = cudaMalloc(&d_val, tb) == cudaSuccess && cudaMalloc(&d_buf[0], tb) == cudaSuccess &&
+             cudaMalloc(&d_buf[1], tb) == cudaSuccess &&
+             cudaMalloc(&d_dm, total * sizeof(double)) == cudaSuccess &&
+             cudaMemcpy(d_val, values, tb, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(d_dm, dmats_cat, total * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            fail(PCB_ENOMEM, "device allocation / upload for the derivative passes failed");
+        }
+    }
+    const double *get(int g) override {
+        if (!ok) return nullptr;
+        const double *cur = d_val;
+        int flip = 0;
+        for (int d = D - 1; d >= 0; --d) {
+            long long outer = 1, inner = 1;
+            for (int e = 0; e < d; ++e) outer *= n[e];
+            for (int e = d + 1; e < D; ++e) inner *= n[e];
+            for (int rep = 0; rep < orders[(size_t)g * D + d]; ++rep) {
+                if (tensor_mode_launch(dev, cur, d_buf[flip], outer, n[d], inner, n[d], d_dm + dm_off[d],
+                                       nullptr) != PCB_OK)
+                    return nullptr;
+                cur = d_buf[flip];
+                flip ^= 1;
+            }
+        }
+        return cur;
+    }
+    const double *host(int g) override {  // only used for small tensors (constant-bank plan)
+        const double *d = get(g);
+        if (!d) return nullptr;
+        h_copy.resize((size_t)size);
+        if (cudaMemcpy(h_copy.data(), d, (size_t)size * sizeof(double), cudaMemcpyDeviceToHost) !=
+            cudaSuccess)
+            return nullptr;
+        return h_copy.data();
+    }
+    ~DerivTensorSource() override {
+        if (d_val) cudaFree(d_val);
+        if (d_buf[0]) cudaFree(d_buf[0]);
+        if (d_buf[1]) cudaFree(d_buf[1]);
+        if (d_dm) cudaFree(d_dm);
+    }
+};
+
+static int full_plan_build(int dev, int D, const int32_t *n, const double *nodes_cat,
+                           const double *weights_cat, int G, TensorSource &src, void **plan) {
     FullPlan *pl = new FullPlan();
     pl->kind = PLAN_FULL;
     pl->dev = dev;
@@ -467,71 +577,117 @@ extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, co
     gd.D = D;
     gd.size = 1;
     for (int d = 0; d < D; ++d) {
-        if (n[d] < 1) {
-            delete pl;
-            return fail(PCB_EINVAL, "n_nodes[%d] must be >= 1", d);
-        }
         gd.n[d] = n[d];
         gd.sum_n += n[d];
         gd.size *= n[d];
     }
-    DeviceGuard guard(dev);
     const size_t nb = (size_t)gd.sum_n * sizeof(double);
     pl->GB = grid_pick_gb(G);
     const int nblk = (G + pl->GB - 1) / pl->GB;
     const size_t tcount = (size_t)gd.size * nblk * pl->GB;
-    if (!guard.ok || cudaMalloc(&pl->d_nodes, 2 * nb) != cudaSuccess ||
+    if (cudaMalloc(&pl->d_nodes, 2 * nb) != cudaSuccess ||
         cudaMalloc(&pl->d_tensors, tcount * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
         delete pl;
         return fail(PCB_ENOMEM, "device allocation for the full-tensor plan failed");
     }
     pl->d_weights = pl->d_nodes + gd.sum_n;
-    bool ok = cudaMemcpy(pl->d_nodes, nodes_cat, nb, cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(pl->d_weights, weights_cat, nb, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (ok) {
-        std::vector<double> il(tcount);
-        grid_interleave(tensors_host, G, pl->GB, gd.size, il.data());
-        ok = cudaMemcpy(pl->d_tensors, il.data(), tcount * sizeof(double), cudaMemcpyHostToDevice) ==
-             cudaSuccess;
-    }
-    if (!ok) {
+    if (cudaMemcpy(pl->d_nodes, nodes_cat, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(pl->d_weights, weights_cat, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(pl->d_tensors, 0, tcount * sizeof(double)) != cudaSuccess) {
         delete pl;
         return fail(PCB_ECUDA, "upload of the full-tensor plan failed");
     }
+    // tensor-core path: prepared copies in fragment order
+    pl->dmma_ok = dmma_configure(pl, n);
+    if (pl->dmma_ok && cudaMalloc(&pl->d_prepared, (size_t)pl->dm.gstride * sizeof(double) * G) != cudaSuccess) {
+        cudaGetLastError();
+        pl->dmma_ok = false;
+    }
+    const bool want_small = D <= 4 && gd.size * G <= 8192;
+    std::vector<std::vector<double>> small_t;
+    const int grid = (int)std::min<long long>((gd.size + 255) / 256, (long long)pl->sm_count * 32);
+    for (int g = 0; g < G; ++g) {
+        const double *t = src.get(g);
+        if (!t) {
+            delete pl;
+            return PCB_ECUDA;  // src.get recorded the message
+        }
+        interleave_kernel<<<grid, 256>>>(t, pl->d_tensors + (size_t)(g / pl->GB) * gd.size * pl->GB,
+                                         gd.size, pl->GB, g % pl->GB);
+        if (pl->dmma_ok) {
+            const int pg = (int)std::min<long long>((pl->dm.gstride + 255) / 256, (long long)pl->sm_count * 32);
+            dmma_prepare_kernel<<<pg, 256>>>(pl->dm, t, pl->d_prepared + (size_t)g * pl->dm.gstride);
+        }
+        if (want_small) {
+            const double *h = src.host(g);
+            if (h) small_t.emplace_back(h, h + gd.size);
+        }
+        // the source reuses its buffers for the next tensor
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            delete pl;
+            return fail(PCB_ECUDA, "preparing tensor %d on the device failed", g);
+        }
+    }
     // small tensors: the constant-bank evaluator of pcb_piecewise.cu through a one-piece spline plan
     // (no knots); kept only if that plan really runs from the bank
-    if (D <= 4 && gd.size * G <= 8192) {
+    if (want_small && (int)small_t.size() == G) {
         std::vector<int32_t> no_knots(D, 0);
+        std::vector<const double *> ptrs;
+        for (auto &v : small_t) ptrs.push_back(v.data());
         if (pcb_spline_plan_create(dev, D, no_knots.data(), nullptr, 1, n, nodes_cat, weights_cat, G,
-                                   tensors_host, &pl->small) != PCB_OK)
+                                   ptrs.data(), &pl->small) != PCB_OK)
             pl->small = nullptr;
         else if (!spline_plan_uses_bank(pl->small)) {
             pcb_plan_destroy(pl->small);
             pl->small = nullptr;
         }
     }
-    // tensor-core path: prepared copies in fragment order
-    pl->dmma_ok = dmma_configure(pl, n);
-    if (pl->dmma_ok) {
-        const size_t pb = (size_t)pl->dm.gstride * sizeof(double);
-        if (cudaMalloc(&pl->d_prepared, pb * G) != cudaSuccess) {
-            cudaGetLastError();
-            pl->dmma_ok = false;
-        } else {
-            std::vector<double> buf((size_t)pl->dm.gstride);
-            for (int g = 0; ok && g < G; ++g) {
-                dmma_prepare(pl->dm, tensors_host[g], buf.data());
-                ok = cudaMemcpy(pl->d_prepared + (size_t)g * pl->dm.gstride, buf.data(), pb,
-                                cudaMemcpyHostToDevice) == cudaSuccess;
-            }
-            if (!ok) {
-                delete pl;
-                return fail(PCB_ECUDA, "upload of the prepared tensors failed");
-            }
-        }
-    }
     *plan = pl;
     return PCB_OK;
+}
+
+static int full_check_shape(int D, const int32_t *n, int G) {
+    PCB_REQUIRE(D >= 1 && D <= GRID_MAXD, "num_dimensions %d outside [1, %d]", D, GRID_MAXD);
+    PCB_REQUIRE(G >= 1 && G <= 64, "number of derivative tensors %d outside [1, 64]", G);
+    for (int d = 0; d < D; ++d) PCB_REQUIRE(n[d] >= 1, "n_nodes[%d] must be >= 1", d);
+    return PCB_OK;
+}
+
+}  // namespace pcb
+
+extern "C" PCB_API int pcb_full_plan_create(int dev, int D, const int32_t *n, const double *nodes_cat,
+                                    const double *weights_cat, int G,
+                                    const double *const *tensors_host, void **plan) {
+    PCB_REQUIRE(plan && n && nodes_cat && weights_cat && tensors_host, "null argument");
+    if (int rc = full_check_shape(D, n, G)) return rc;
+    DeviceGuard guard(dev);
+    if (!guard.ok) return fail(PCB_ECUDA, "cannot select device %d", dev);
+    long long size = 1;
+    for (int d = 0; d < D; ++d) size *= n[d];
+    HostTensorSource src(tensors_host, size);
+    return full_plan_build(dev, D, n, nodes_cat, weights_cat, G, src, plan);
+}
+
+extern "C" PCB_API int pcb_full_plan_create_from_values(int dev, int D, const int32_t *n,
+                                                        const double *nodes_cat,
+                                                        const double *weights_cat,
+                                                        const double *diffmats_cat,
+                                                        const double *values_host, int G,
+                                                        const int32_t *orders, void **plan) {
+    PCB_REQUIRE(plan && n && nodes_cat && weights_cat && diffmats_cat && values_host && orders,
+                "null argument");
+    if (int rc = full_check_shape(D, n, G)) return rc;
+    for (int d = 0; d < D; ++d) PCB_REQUIRE(n[d] <= 64, "n_nodes[%d] = %d exceeds 64", d, n[d]);
+    for (int i = 0; i < G * D; ++i)
+        PCB_REQUIRE(orders[i] >= 0 && orders[i] <= 8, "derivative order %d outside [0, 8]", orders[i]);
+    DeviceGuard guard(dev);
+    if (!guard.ok) return fail(PCB_ECUDA, "cannot select device %d", dev);
+    long long size = 1;
+    for (int d = 0; d < D; ++d) size *= n[d];
+    DerivTensorSource src(dev, D, n, diffmats_cat, values_host, orders, size);
+    if (!src.ok) return PCB_ENOMEM;
+    return full_plan_build(dev, D, n, nodes_cat, weights_cat, G, src, plan);
 }
 
 template <int KB>

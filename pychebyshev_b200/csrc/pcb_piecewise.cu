@@ -94,7 +94,7 @@ constexpr int LOOKUP_ILP = 2, LOOKUP_MAXD = 4;
 __global__ void __launch_bounds__(256, 8)
 spline_lookup_kernel(int D, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
                      const double *__restrict__ knots, const double *__restrict__ pts, int64_t N,
-                     int32_t *__restrict__ piece) {
+                     int32_t *__restrict__ piece, int aligned16) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x * LOOKUP_ILP;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x * LOOKUP_ILP + threadIdx.x; base < N; base += step) {
         if (D > LOOKUP_MAXD) {  // uniform: generic path straight from memory
@@ -109,7 +109,7 @@ spline_lookup_kernel(int D, const int *__restrict__ num_knots, const int *__rest
 #pragma unroll
         for (int k = 0; k < LOOKUP_ILP; ++k) {
             const int64_t q = base + (int64_t)k * blockDim.x;
-            if (D == 2) {
+            if (D == 2 && aligned16) {  // 128-bit loads need a 16-byte aligned base (uniform branch)
                 const double2 v = q < N ? __ldg(reinterpret_cast<const double2 *>(pts) + q) : make_double2(0.0, 0.0);
                 x[k][0] = v.x;
                 x[k][1] = v.y;
@@ -808,7 +808,8 @@ extern "C" PCB_API int pcb_spline_lookup(void *plan, const double *d_points, int
     const int64_t want = (N + 256 * LOOKUP_ILP - 1) / (256 * LOOKUP_ILP);
     const int64_t cap = (int64_t)pl->sm_count * 8;
     spline_lookup_kernel<<<(int)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        pl->D, pl->d_num_knots, pl->d_knot_off, pl->d_knots, d_points, N, d_piece);
+        pl->D, pl->d_num_knots, pl->d_knot_off, pl->d_knots, d_points, N, d_piece,
+        (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 ? 1 : 0);
     g_launches.fetch_add(1);
     PCB_CUDA(cudaGetLastError());
     return PCB_OK;

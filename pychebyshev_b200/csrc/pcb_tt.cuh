@@ -85,7 +85,7 @@ struct TTPlan : PlanBase {
     // uniform-datapath path (cores in the constant bank), when the train is small enough:
     // values need the forward cores, the shared-FD kernel the transposed copies as well
     bool const_value_ok = false, const_shared_ok = false;
-    int const_qpt = 2, const_threads_value = 512, const_threads_shared = 512;
+    int const_qpt_value = 2, const_qpt_shared = 2, const_threads_value = 512, const_threads_shared = 512;
     // Constant-bank images (pcb_tt_const.cu).  The 8192-double bank holds only the cores a launch
     // reads: all forward cores for values; for price+Greeks the forward cores left of the last
     // differentiated dim, the transposed cores right of the first, and each differentiated core in
@@ -100,7 +100,6 @@ struct TTPlan : PlanBase {
     int core_off[PCB_MAX_DIMS + 1] = {0};
     std::mutex image_mutex;
     std::map<uint64_t, ConstImage> images;  // key: need_fwd mask | need_T mask << 32
-    bool last_fd_const = false;
     // per-core launches with the chain state in global memory (large trains, pcb_tt_const.cu)
     bool gstream_ok = false, gstream_fd_ok = false;  // values / price+Greeks (shared-memory limits)
     std::map<int, ConstImage> gimages;  // key 2 k + orientation; coff[c] chunk bases, coffT[c] widths
@@ -132,6 +131,8 @@ int ttc_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_ou
                      bool *fits);
 int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
                       double *d_out, cudaStream_t st, bool *fits);
+int ttc_shared_fits(TTPlan *pl, const TTSharedProgram &prog);  // 0 no, 1 one launch, 2 per dim
+bool ttg_shared_fits(const TTPlan *pl, const TTSharedProgram &prog);
 // one launch per core, chain state in global memory (trains whose single cores fit in the bank)
 int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st);
 int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,

@@ -569,14 +569,57 @@ static TTParams ttc_params(const TTPlan *pl, const TTPlan::ConstImage *img) {
     return P;
 }
 
-#define TTC_VALUE(Q, R)                                                                           \
-    if (pl->const_qpt == Q && rc_ == R)                                                           \
-        return ttc_launch(ttc_value_kernel<Q, R, 512>, pl, img, Q, threads, 1, N, st, P, d_points, N, \
-                          d_out);
-#define TTC_SHARED(Q, R, T)                                                                       \
-    if (pl->const_qpt == Q && rc_ == R && threads <= T)                                           \
-        return ttc_launch(ttc_fd_shared_kernel<Q, R, T>, pl, img, Q, threads, 2, N, st, P, prog,    \
-                          d_points, N, d_out);
+// Kernel variants (query slots per thread, rank class, threads per CTA = launch bound).  The plan
+// asks for (qpt, threads); an exact match is used when it exists and fits, otherwise the first
+// variant of the plan's rank class whose chain-vector buffers fit in shared memory.
+template <int Q, int R, int T>
+static int ttc_value_go(const TTPlan *pl, const TTPlan::ConstImage *img, const TTParams &P,
+                        const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+    return ttc_launch(ttc_value_kernel<Q, R, T>, pl, img, Q, T, 1, N, st, P, d_points, N, d_out);
+}
+template <int Q, int R, int T>
+static int ttc_shared_go(const TTPlan *pl, const TTPlan::ConstImage *img, const TTParams &P,
+                         const TTSharedProgram &prog, const double *d_points, int64_t N,
+                         double *d_out, cudaStream_t st) {
+    return ttc_launch(ttc_fd_shared_kernel<Q, R, T>, pl, img, Q, T, 2, N, st, P, prog, d_points, N,
+                      d_out);
+}
+struct TTCValueVariant {
+    int q, r, t;
+    int (*go)(const TTPlan *, const TTPlan::ConstImage *, const TTParams &, const double *, int64_t,
+              double *, cudaStream_t);
+};
+struct TTCSharedVariant {
+    int q, r, t;
+    int (*go)(const TTPlan *, const TTPlan::ConstImage *, const TTParams &, const TTSharedProgram &,
+              const double *, int64_t, double *, cudaStream_t);
+};
+#define VV(Q, R, T) {Q, R, T, ttc_value_go<Q, R, T>}
+#define SV(Q, R, T) {Q, R, T, ttc_shared_go<Q, R, T>}
+// first entry of a rank class = its default
+static const TTCValueVariant kValueVariants[] = {
+    VV(2, 8, 512), VV(2, 12, 512), VV(2, 16, 512),
+    VV(3, 12, 320), VV(4, 12, 256), VV(4, 8, 256), VV(3, 16, 320),
+};
+static const TTCSharedVariant kSharedVariants[] = {
+    SV(2, 8, 512), SV(2, 12, 512), SV(2, 16, 384),
+    SV(2, 12, 384), SV(3, 12, 320), SV(3, 12, 256), SV(4, 12, 256), SV(4, 12, 192),
+    SV(4, 8, 256), SV(3, 16, 256),
+};
+#undef VV
+#undef SV
+
+template <typename V, size_t NV>
+static const V *ttc_pick(const V (&tab)[NV], const TTPlan *pl, int qpt, int threads, int rc_, int nbuf) {
+    auto fits = [&](const V &v) {
+        return (size_t)nbuf * pl->P.rmaxp * v.q * v.t * sizeof(double) <= (size_t)pl->smem_optin;
+    };
+    for (const V &v : tab)
+        if (v.q == qpt && v.r == rc_ && v.t == threads && fits(v)) return &v;
+    for (const V &v : tab)
+        if (v.r == rc_ && fits(v)) return &v;
+    return nullptr;
+}
 
 int ttc_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st,
                      bool *fits) {
@@ -585,9 +628,10 @@ int ttc_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_ou
     *fits = img != nullptr;
     if (!img) return PCB_OK;
     const TTParams P = ttc_params(pl, img);
-    const int threads = pl->const_threads_value, rc_ = ttc_rank_class(pl);
-    TTC_VALUE(2, 8) TTC_VALUE(2, 12) TTC_VALUE(2, 16) TTC_VALUE(1, 8) TTC_VALUE(1, 12) TTC_VALUE(1, 16)
-    return fail(PCB_EUNSUPPORTED, "no uniform-path TT value kernel for this configuration");
+    const TTCValueVariant *v = ttc_pick(kValueVariants, pl, pl->const_qpt_value, pl->const_threads_value,
+                                        ttc_rank_class(pl), 1);
+    if (!v) return fail(PCB_EUNSUPPORTED, "no uniform-path TT value kernel for this configuration");
+    return v->go(pl, img, P, d_points, N, d_out, st);
 }
 
 // cores ttc_fd_shared_kernel reads for `prog`: left sweep up to the last slot, right sweeps down to
@@ -609,33 +653,21 @@ static void ttc_shared_need(const TTPlan *pl, const TTSharedProgram &prog, uint6
 
 static int ttc_launch_shared_one(TTPlan *pl, const TTPlan::ConstImage *img, const TTSharedProgram &prog,
                                  const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
-    // both chain-vector buffers must fit in shared memory
-    int threads = pl->const_threads_shared;
-    while ((size_t)2 * pl->P.rmaxp * pl->const_qpt * threads * 8 > (size_t)pl->smem_optin && threads > 128)
-        threads -= 128;
     const TTParams P = ttc_params(pl, img);
-    const int rc_ = ttc_rank_class(pl);
-    TTC_SHARED(2, 8, 256) TTC_SHARED(2, 12, 256) TTC_SHARED(2, 16, 256)
-    TTC_SHARED(2, 8, 384) TTC_SHARED(2, 12, 384) TTC_SHARED(2, 16, 384)
-    TTC_SHARED(2, 8, 512) TTC_SHARED(2, 12, 512) TTC_SHARED(2, 16, 512)
-    TTC_SHARED(1, 8, 512) TTC_SHARED(1, 12, 512) TTC_SHARED(1, 16, 512)
-    return fail(PCB_EUNSUPPORTED, "no uniform-path TT shared-FD kernel for this configuration");
+    // both chain-vector buffers must fit in shared memory (ttc_pick checks)
+    const TTCSharedVariant *v = ttc_pick(kSharedVariants, pl, pl->const_qpt_shared,
+                                         pl->const_threads_shared, ttc_rank_class(pl), 2);
+    if (!v) return fail(PCB_EUNSUPPORTED, "no uniform-path TT shared-FD kernel for this configuration");
+    return v->go(pl, img, P, prog, d_points, N, d_out, st);
 }
 
-int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
-                      double *d_out, cudaStream_t st, bool *fits) {
-    uint64_t need_fwd, need_T;
-    ttc_shared_need(pl, prog, &need_fwd, &need_T);
-    const TTPlan::ConstImage *img = pl->const_image(need_fwd, need_T);
-    *fits = img != nullptr;
-    if (img) return ttc_launch_shared_one(pl, img, prog, d_points, N, d_out, st);
-    if (prog.n_slots < 2) return PCB_OK;
-    // The union does not fit (Greeks at both ends of a long train need every core in both
-    // orientations): one launch per differentiated dim, each with its own image and writing only
-    // its own output rows (value rows go with the first).  Left sweeps restart per launch.
+// Split of a Greek set whose union of cores does not fit the bank (Greeks at both ends of a long
+// train need every core in both orientations): one sub-program per differentiated dim, each with
+// its own image and writing only its own output rows (value rows go with the first).
+static bool ttc_split(TTPlan *pl, const TTSharedProgram &prog, TTSharedProgram *sub,
+                      const TTPlan::ConstImage **imgs) {
     constexpr int SKIP = 1 << 20;  // row_slot that matches no slot and is not a value row
-    TTSharedProgram sub[TT_MAX_G];
-    const TTPlan::ConstImage *imgs[TT_MAX_G];
+    if (prog.n_slots < 2) return false;
     for (int t = 0; t < prog.n_slots; ++t) {
         sub[t].G = prog.G;
         sub[t].n_slots = 1;
@@ -645,12 +677,37 @@ int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_p
             sub[t].row_slot[g] = rs == t ? 0 : ((rs < 0 && t == 0) ? -1 : SKIP);
             sub[t].row_ord[g] = prog.row_ord[g];
         }
+        uint64_t need_fwd, need_T;
         ttc_shared_need(pl, sub[t], &need_fwd, &need_T);
         imgs[t] = pl->const_image(need_fwd, need_T);
-        if (!imgs[t]) return PCB_OK;  // *fits stays false: shared-memory kernel
+        if (!imgs[t]) return false;
     }
+    return true;
+}
+
+// 0: does not fit the bank; 1: one launch; 2: one launch per differentiated dim
+int ttc_shared_fits(TTPlan *pl, const TTSharedProgram &prog) {
+    if (!pl->const_enabled) return 0;
+    uint64_t need_fwd, need_T;
+    ttc_shared_need(pl, prog, &need_fwd, &need_T);
+    if (pl->const_image(need_fwd, need_T)) return 1;
+    TTSharedProgram sub[TT_MAX_G];
+    const TTPlan::ConstImage *imgs[TT_MAX_G];
+    return ttc_split(pl, prog, sub, imgs) ? 2 : 0;
+}
+
+int ttc_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
+                      double *d_out, cudaStream_t st, bool *fits) {
+    uint64_t need_fwd, need_T;
+    ttc_shared_need(pl, prog, &need_fwd, &need_T);
+    const TTPlan::ConstImage *img = pl->const_image(need_fwd, need_T);
+    *fits = img != nullptr;
+    if (img) return ttc_launch_shared_one(pl, img, prog, d_points, N, d_out, st);
+    TTSharedProgram sub[TT_MAX_G];
+    const TTPlan::ConstImage *imgs[TT_MAX_G];
+    if (!ttc_split(pl, prog, sub, imgs)) return PCB_OK;  // *fits stays false: shared-memory kernel
     *fits = true;
-    for (int t = 0; t < prog.n_slots; ++t)
+    for (int t = 0; t < prog.n_slots; ++t)  // left sweeps restart per launch
         if (int rc = ttc_launch_shared_one(pl, imgs[t], sub[t], d_points, N, d_out, st)) return rc;
     return PCB_OK;
 }
@@ -744,26 +801,46 @@ static int ttg_step(TTPlan *pl, int k, int orient, const double *s_in, double *s
                       tile_n, d_points, N, st);
 }
 
-struct TTGScratch {  // stream-ordered scratch for the chain states of one tile
+// Stream-ordered scratch for the chain states of one tile, from a PRIVATE memory pool owned by
+// this library (one per device, created on first use).  The pool keeps up to TTG_POOL_KEEP bytes
+// across calls (a default-threshold pool hands everything back to the driver at every
+// synchronisation, i.e. a fresh allocation per call); the device's default pool and PyTorch's
+// caching allocator are left untouched.
+constexpr uint64_t TTG_POOL_KEEP = 6ull << 30;
+static cudaMemPool_t ttg_pool(int dev) {
+    static std::mutex m;
+    static cudaMemPool_t pools[ConstBank::MAX_DEV] = {nullptr};
+    if (dev < 0 || dev >= ConstBank::MAX_DEV) return nullptr;
+    std::lock_guard<std::mutex> lock(m);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        uint64_t keep = TTG_POOL_KEEP;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = pool;
+    }
+    return pools[dev];
+}
+
+struct TTGScratch {
     double *p = nullptr;
     cudaStream_t st;
     TTGScratch(int dev, size_t doubles, cudaStream_t s) : st(s) {
-        // keep freed scratch in the device's default pool (the default threshold 0 hands it back
-        // to the driver at every synchronisation, i.e. a fresh allocation per call)
-        static std::mutex m;
-        static bool tuned[ConstBank::MAX_DEV] = {false};
-        {
-            std::lock_guard<std::mutex> lock(m);
-            if (dev >= 0 && dev < ConstBank::MAX_DEV && !tuned[dev]) {
-                cudaMemPool_t pool;
-                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                    uint64_t keep = UINT64_MAX;
-                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                }
-                tuned[dev] = true;
-            }
+        cudaMemPool_t pool = ttg_pool(dev);
+        const cudaError_t e = pool ? cudaMallocFromPoolAsync(&p, doubles * sizeof(double), pool, s)
+                                   : cudaMallocAsync(&p, doubles * sizeof(double), s);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
         }
-        if (cudaMallocAsync(&p, doubles * sizeof(double), s) != cudaSuccess) p = nullptr;
     }
     ~TTGScratch() {
         if (p) cudaFreeAsync(p, st);
@@ -795,17 +872,23 @@ int ttg_launch_value(TTPlan *pl, const double *d_points, int64_t N, double *d_ou
     return PCB_OK;
 }
 
+bool ttg_shared_fits(const TTPlan *pl, const TTSharedProgram &prog) {
+    if (!pl->gstream_fd_ok) return false;
+    for (int t = 0; t < prog.n_slots; ++t) {
+        const int a = prog.slot_dim[t];
+        const size_t smem = (size_t)(pl->P.r[a] + pl->P.r[a + 1] + pl->P.n[a]) * TTG_QPT *
+                            TTG_THREADS_COEFF * sizeof(double);
+        if (smem > (size_t)pl->smem_optin) return false;
+    }
+    return true;
+}
+
 int ttg_launch_shared(TTPlan *pl, const TTSharedProgram &prog, const double *d_points, int64_t N,
                       double *d_out, cudaStream_t st, bool *fits) {
     const TTParams &P = pl->P;
     const int D = P.D;
     // the coefficient pass of every differentiated dim keeps r_rows + r_acc + n rows in shared memory
-    *fits = true;
-    for (int t = 0; t < prog.n_slots; ++t) {
-        const int a = prog.slot_dim[t];
-        const size_t smem = (size_t)(P.r[a] + P.r[a + 1] + P.n[a]) * TTG_QPT * TTG_THREADS_COEFF * sizeof(double);
-        if (smem > (size_t)pl->smem_optin) *fits = false;
-    }
+    *fits = ttg_shared_fits(pl, prog);
     if (!*fits) return PCB_OK;  // caller falls back to the shared-memory kernels
     const int64_t tile = std::min<int64_t>((int64_t)TTG_WAVES * pl->sm_count * 1024, (N + 1023) / 1024 * 1024);
     const int rmax = ttg_rmax(pl);

@@ -211,12 +211,13 @@ extern "C" PCB_API int pcb_tt_plan_create(int dev, int D, const int32_t *n, cons
                         for (int l = 0; l < ranks[k + 1]; ++l)
                             pl->h_T[(size_t)pl->core_off[k] + ((size_t)l * n[k] + j) * ranks[k] + i] =
                                 cores_cat[s2++];
-            pl->const_qpt = env_int("PCB_TT_QPT", 2) == 1 ? 1 : 2;
-            const int t = env_int("PCB_TT_THREADS", 512);
-            pl->const_threads_value = t;
-            pl->const_threads_shared = t;
+            // (qpt, threads) of the uniform-path kernels; ttc_pick falls back to the rank class's
+            // default variant when the pair is not compiled in or does not fit in shared memory
+            pl->const_qpt_value = env_int("PCB_TT_QPT_VALUE", env_int("PCB_TT_QPT", 2));
+            pl->const_qpt_shared = env_int("PCB_TT_QPT_FD", env_int("PCB_TT_QPT", 2));
+            pl->const_threads_value = env_int("PCB_TT_THREADS_VALUE", env_int("PCB_TT_THREADS", 512));
+            pl->const_threads_shared = env_int("PCB_TT_THREADS_FD", env_int("PCB_TT_THREADS", 512));
         }
-        pl->last_fd_const = pl->const_shared_ok;
         // large trains: every single core fits in the bank -> one launch per core
         bool each_fits = env_int("PCB_TT_CONST", 1) != 0 && env_int("PCB_TT_GSTREAM", 1) != 0 && rmax <= 64;
         for (int k = 0; k < D; ++k)
@@ -296,8 +297,8 @@ extern "C" PCB_API int pcb_tt_plan_info(void *plan, int32_t *out8) {
     TTPlan *pl = static_cast<TTPlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_TT && out8, "not a TT plan");
     out8[0] = pl->const_value_ok;
-    out8[1] = pl->last_fd_const;  // did the last price+Greeks launch run from the constant bank?
-    out8[2] = pl->const_qpt;
+    out8[1] = pl->const_shared_ok;  // every Greek set fits the bank (per set: pcb_tt_fd_path)
+    out8[2] = pl->const_qpt_shared;
     out8[3] = pl->const_threads_value;
     out8[4] = pl->const_threads_shared;
     out8[5] = pl->cfg_chain.mode;
@@ -314,6 +315,24 @@ extern "C" PCB_API int pcb_tt_fd_algo(void *plan, int G, const int32_t *orders) 
     if (int rc = tt_build_program(pl, G, orders, &prog)) return rc;
     TTSharedProgram sp;
     return tt_build_shared_program(prog, &sp) ? 2 : 1;
+}
+
+// Which kernel family pcb_tt_eval_fd runs for these rows (reporting only; evaluation itself keeps
+// no state): 1 one chain per stencil point (general rows), 2 constant-bank shared-product kernel
+// (one launch), 3 the same with one launch per differentiated dim, 4 per-core launches (large
+// trains), 5 shared-memory shared-product kernel.
+extern "C" PCB_API int pcb_tt_fd_path(void *plan, int G, const int32_t *orders, int algo) {
+    TTPlan *pl = static_cast<TTPlan *>(plan);
+    PCB_REQUIRE(pl && pl->kind == PLAN_TT, "not a TT plan");
+    PCB_REQUIRE(orders, "null orders");
+    TTFdProgram prog;
+    if (int rc = tt_build_program(pl, G, orders, &prog)) return rc;
+    TTSharedProgram sp;
+    const bool can_share = tt_build_shared_program(prog, &sp);
+    if (!(algo == 2 || (algo == 0 && can_share)) || !can_share) return 1;
+    if (const int f = ttc_shared_fits(pl, sp)) return 1 + f;
+    if (ttg_shared_fits(pl, sp)) return 4;
+    return 5;
 }
 
 extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_t N, int G,
@@ -339,12 +358,10 @@ extern "C" PCB_API int pcb_tt_eval_fd(void *plan, const double *d_points, int64_
         bool fits = false;
         if (pl->const_enabled) {
             const int rc = ttc_launch_shared(pl, sp, d_points, N, d_out, st, &fits);
-            pl->last_fd_const = fits;
             if (rc || fits) return rc;
         }
         if (pl->gstream_fd_ok) {
             const int rc = ttg_launch_shared(pl, sp, d_points, N, d_out, st, &fits);
-            pl->last_fd_const = fits;
             if (rc || fits) return rc;
         }
         return tt_launch_shared(pl, sp, d_points, N, d_out, st);

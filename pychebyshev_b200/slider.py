@@ -16,7 +16,7 @@ from typing import List
 import numpy as np
 
 from . import _grid
-from ._engine import SliderPlan, require_device
+from ._engine import SliderPlan, fingerprint, require_device
 from .approximation import ChebyshevApproximation, _DerivativeIds, _unwrap
 
 
@@ -93,7 +93,7 @@ class ChebyshevSlider(_DerivativeIds):
     def _plan(self, orders, device=None) -> SliderPlan:
         orders = _grid.normalize_orders(orders, self.num_dimensions)
         dev = require_device(self.device if device is None else device)
-        token = tuple(id(s.tensor_values) for s in self.slides) + (float(self.pivot_value),)
+        token = tuple(fingerprint(s.tensor_values) for s in self.slides) + (float(self.pivot_value),)
         key = (dev, orders)
         hit = self._plans.get(key)
         if hit is None or hit[0] != token:

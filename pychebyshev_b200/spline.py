@@ -17,7 +17,7 @@ from typing import List
 import numpy as np
 
 from . import _grid, pcbfile
-from ._engine import SplinePlan, require_device
+from ._engine import SplinePlan, fingerprint, require_device
 from .approximation import ChebyshevApproximation, _DerivativeIds, _unwrap
 
 KNOT_EPS = 1e-14  # reference spline.py:545
@@ -233,7 +233,7 @@ class ChebyshevSpline(_DerivativeIds):
     def _plan(self, orders, device=None) -> SplinePlan:
         orders = _grid.normalize_orders(orders, self.num_dimensions)
         dev = require_device(self.device if device is None else device)
-        token = tuple(id(p.tensor_values) for p in self._pieces)
+        token = tuple(fingerprint(p.tensor_values) for p in self._pieces)
         key = (dev, orders)
         hit = self._plans.get(key)
         if hit is None or hit[0] != token:

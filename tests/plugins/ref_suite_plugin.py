@@ -1,0 +1,35 @@
+"""pytest plugin: run the REFERENCE's own test files with the B200 backend swapped in.
+
+Loaded with ``-p ref_suite_plugin`` by tests/test_reference_suite.py (the reference's
+tests all go through the evaluation methods, so they are a free regression suite for the drop-in).
+It imports the unmodified reference (oracle/_ref/site), rebinds its vectorised evaluation methods
+to the CUDA engine (``pychebyshev_b200.dropin.install``) and reports how many kernels ran.
+"""
+
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+_before = 0
+
+
+def pytest_configure(config):
+    global _before
+    from oracle import reference as R
+
+    ref = R.load()
+    from pychebyshev_b200 import _engine, dropin
+
+    dropin.install(ref)
+    _before = _engine.launch_count()
+
+
+def pytest_terminal_summary(terminalreporter):
+    from pychebyshev_b200 import _engine, dropin
+
+    n = _engine.launch_count() - _before
+    terminalreporter.write_line(
+        f"B200_BACKEND installed={dropin.installed()} kernel_launches={n}")

@@ -49,12 +49,14 @@ print(json.dumps(res))
 
 
 def main():
-    configs = [tuple(int(v) for v in c.split('x')) for c in os.environ.get('TT_CONFIGS', '0x0,2x256,2x384,2x512,1x512,3x256,3x384,4x256').split(',')]
+    configs = [tuple(int(v) for v in c.split('x')) for c in os.environ.get('TT_CONFIGS', '0x0,2x512,2x384,3x320,3x256,4x256,4x192').split(',')]
     for q, t in configs:
         env = dict(os.environ)
         if q:
-            env["PCB_TT_QPT"], env["PCB_TT_THREADS"] = str(q), str(t)
-        env["TT_SKIP_FD1"] = "1" if q else ""
+            # uniform-path (constant-bank) kernels only; the shared-memory kernels keep their own pick
+            for suffix in ("_FD", "_VALUE"):
+                env["PCB_TT_QPT" + suffix], env["PCB_TT_THREADS" + suffix] = str(q), str(t)
+        env["TT_SKIP_FD1"] = "1"
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr.strip()[-300:]
         try:
