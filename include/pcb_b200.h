@@ -201,6 +201,30 @@ PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64_t N, doubl
  * ------------------------------------------------------------------------------------------ */
 PCB_API int pcb_plan_from_file(int dev, const char *path, void **plan, int *kind, int *D);
 
+/* The same with G derivative-order rows (G x D int32, HOST): a plan with G outputs per point.  The
+ * differentiation matrices follow barycentric.py:52-77 (row sums in NumPy's pairwise order); the
+ * derivative tensors are made by the passes of barycentric.py:982-989 -- on the device for
+ * approximations (pcb_full_plan_create_from_values), on the host for the small spline pieces.
+ * G = 0 / orders = NULL: values only. */
+PCB_API int pcb_plan_from_file_orders(int dev, const char *path, int G, const int32_t *orders, void **plan,
+                              int *kind, int *D);
+
+/* Native .pcb WRITER (reference _binary.py:208-236, 289-346): byte-identical files.
+ *   pcb_file_write_approx : ChebyshevApproximation (domain lo/hi, n_nodes, C-order tensor)
+ *   pcb_file_write_spline : ChebyshevSpline with flat n_nodes (knots concatenated over dims,
+ *                           P = prod(num_knots + 1) piece tensors in C-order)
+ *   pcb_file_rewrite      : read in_path with the native parser and write it back (round trip) */
+PCB_API int pcb_file_write_approx(const char *path, int D, const double *lo, const double *hi,
+                          const int32_t *n, const double *tensor);
+PCB_API int pcb_file_write_spline(const char *path, int D, const double *lo, const double *hi,
+                          const int32_t *n, const int32_t *num_knots, const double *knots_cat, int P,
+                          const double *const *piece_tensors);
+PCB_API int pcb_file_rewrite(const char *in_path, const char *out_path);
+
+/* Nodes, barycentric weights and (optionally, dmat != NULL) the n x n differentiation matrix the
+ * native loader derives for one dimension (reporting / tests). */
+PCB_API int pcb_file_grid_arrays(double lo, double hi, int n, double *nodes, double *weights, double *dmat);
+
 /* Values of any plan kind (the plan's own number of outputs per point). */
 PCB_API int pcb_plan_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream);
 

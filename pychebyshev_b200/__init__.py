@@ -19,12 +19,13 @@ from .tt import ChebyshevTT
 __version__ = "0.1.0"
 
 
-def load_plan(path, device=None):
-    """Native ``.pcb`` -> device value plan (``plan.eval(points)`` -> (N, 1)); see
-    ``pcb_plan_from_file`` in ``include/pcb_b200.h``."""
+def load_plan(path, device=None, orders=None):
+    """Native ``.pcb`` -> device plan (``plan.eval(points)`` -> (N, G)); ``orders``: optional list of
+    derivative-order rows (values only otherwise).  See ``pcb_plan_from_file[_orders]`` in
+    ``include/pcb_b200.h``."""
     from ._engine import FilePlan
 
-    return FilePlan(path, device)
+    return FilePlan(path, device, orders)
 
 
 @dataclass(frozen=True)

@@ -497,22 +497,61 @@ class SliderPlan(DevicePlan):
 
 
 class FilePlan(DevicePlan):
-    """A value plan built natively from a ``.pcb`` file (``pcb_plan_from_file``): no Python
-    object, no NumPy grid arithmetic -- the C++ twin of the reference's stand-alone readers."""
+    """A plan built natively from a ``.pcb`` file (``pcb_plan_from_file[_orders]``): no Python
+    object, no NumPy grid arithmetic -- the C++ twin of the reference's stand-alone readers.
+    ``orders``: optional G derivative-order rows -> G outputs per point (values only otherwise)."""
 
-    def __init__(self, path, device=None):
+    def __init__(self, path, device=None, orders=None):
         import os
 
         lib = _lib.load()
         dev = require_device(device)
         handle, kind, ndim = C.c_void_p(), C.c_int32(), C.c_int32()
-        _lib.check(lib.pcb_plan_from_file(dev, os.fsencode(os.fspath(path)), C.byref(handle),
-                                          C.byref(kind), C.byref(ndim)))
-        super().__init__(handle, dev, int(ndim.value), 1)
+        fs = os.fsencode(os.fspath(path))
+        if orders is None:
+            _lib.check(lib.pcb_plan_from_file(dev, fs, C.byref(handle), C.byref(kind), C.byref(ndim)))
+            G = 1
+        else:
+            arr = np.ascontiguousarray(np.asarray(orders, dtype=np.int32))
+            if arr.ndim != 2:
+                raise ValueError("orders must be a list of derivative-order rows")
+            G = arr.shape[0]
+            with open(os.fspath(path), "rb") as f:
+                head = f.read(16)
+            ndim_file = int.from_bytes(head[12:16], "little") if len(head) == 16 else -1
+            if ndim_file != arr.shape[1]:
+                raise ValueError(
+                    f"derivative rows have {arr.shape[1]} entries, file has {ndim_file} dimensions")
+            _lib.check(lib.pcb_plan_from_file_orders(dev, fs, G, arr.ctypes.data_as(_lib._i32p),
+                                                     C.byref(handle), C.byref(kind), C.byref(ndim)))
+        super().__init__(handle, dev, int(ndim.value), G)
         self.kind = {1: "approx", 2: "spline"}[int(kind.value)]
 
     def _launch(self, d_points, n, d_out, stream):
         _lib.check(_lib.load().pcb_plan_eval(self._handle, d_points, n, d_out, stream))
+
+
+def write_pcb_native(path, domain, n_nodes, tensors, knots=None) -> None:
+    """``.pcb`` v1 through the NATIVE writer (``pcb_file_write_approx`` / ``_spline``): one tensor
+    for an approximation, the C-order piece tensors (+ ``knots``) for a spline."""
+    import os
+
+    lib = _lib.load()
+    D = len(n_nodes)
+    _, lo_p = _lib.as_f64([float(d[0]) for d in domain])
+    _, hi_p = _lib.as_f64([float(d[1]) for d in domain])
+    _, n_p = _lib.as_i32(n_nodes)
+    fs = os.fsencode(os.fspath(path))
+    if knots is None:
+        t = np.ascontiguousarray(tensors, dtype=np.float64)
+        _lib.check(lib.pcb_file_write_approx(fs, D, lo_p, hi_p, n_p, t.ctypes.data_as(_lib._f64p)))
+        return
+    keep = [np.ascontiguousarray(t, dtype=np.float64) for t in tensors]
+    _, nk_p = _lib.as_i32([len(k) for k in knots])
+    kcat = [float(v) for k in knots for v in k]
+    _, k_p = _lib.as_f64(kcat if kcat else [0.0])
+    _lib.check(lib.pcb_file_write_spline(fs, D, lo_p, hi_p, n_p, nk_p, k_p, len(keep),
+                                         _lib.ptr_array(keep)))
 
 
 def probe_fp64_peak(kind: int, device=None):

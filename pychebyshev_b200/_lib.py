@@ -60,6 +60,12 @@ SIGNATURES = {
                                          C.c_double, C.c_int, _i32p, C.POINTER(_f64p), _vpp]),
     "pcb_slider_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pcb_plan_from_file": (C.c_int, [C.c_int, C.c_char_p, _vpp, _i32p, _i32p]),
+    "pcb_plan_from_file_orders": (C.c_int, [C.c_int, C.c_char_p, C.c_int, _i32p, _vpp, _i32p, _i32p]),
+    "pcb_file_write_approx": (C.c_int, [C.c_char_p, C.c_int, _f64p, _f64p, _i32p, _f64p]),
+    "pcb_file_write_spline": (C.c_int, [C.c_char_p, C.c_int, _f64p, _f64p, _i32p, _i32p, _f64p,
+                                        C.c_int, C.POINTER(_f64p)]),
+    "pcb_file_rewrite": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "pcb_file_grid_arrays": (C.c_int, [C.c_double, C.c_double, C.c_int, _f64p, _f64p, _f64p]),
     "pcb_plan_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pcb_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "pcb_launch_count": (C.c_int64, []),

@@ -261,7 +261,11 @@ class ChebyshevApproximation(_DerivativeIds):
         if key not in self._plans:
             if len(self._plans) >= 8:  # bound device memory held by stale order sets
                 self._plans.pop(next(iter(self._plans)))
-            if os.environ.get("PCB_DEVICE_DERIV", "1") != "0" and max(self.n_nodes) <= 64:
+            # (1-D tensors stay on the host recipe: NumPy runs `vector @ D^T` through dgemv, whose
+            # lane-split partial sums differ from the chain in the last bit -- and a 1-D tensor is
+            # tiny anyway)
+            if (os.environ.get("PCB_DEVICE_DERIV", "1") != "0" and max(self.n_nodes) <= 64
+                    and self.num_dimensions >= 2):
                 # N3: one upload of the value tensor, derivative tensors made on the device
                 self._plans[key] = FullPlan.from_values(
                     self.n_nodes, self.nodes, self.weights, self.diff_matrices, self.tensor_values,

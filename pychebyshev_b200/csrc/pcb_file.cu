@@ -141,16 +141,204 @@ static void make_weights(const double *x, int n, double *w) {
     }
 }
 
+// numpy's pairwise summation of a contiguous row (np.sum over the last axis): < 8 sequential,
+// otherwise 8 interleaved partial sums combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a
+// sequential tail; rows longer than 128 split recursively.
+static double np_pairwise_sum(const double *a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// barycentric.py:52-77: D_ij = w_j / ((x_i - x_j) * w_i), diagonal = -(row sum)
+static void make_diff_matrix(const double *x, const double *w, int n, double *dm) {
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+            const double c = i == j ? 1.0 : x[i] - x[j];
+            dm[(size_t)i * n + j] = i == j ? 0.0 : w[j] / (c * w[i]);
+        }
+        dm[(size_t)i * n + i] = -np_pairwise_sum(dm + (size_t)i * n, n);
+    }
+}
+
+// One pass of _apply_derivative_passes on the host (small spline pieces): the same sequential FMA
+// chain as the device kernel (pcb_tensor.cu) and OpenBLAS.
+static void host_deriv_pass(const double *src, double *dst, long long outer, int n, long long inner,
+                            const double *dm) {
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner; ++i)
+            for (int j = 0; j < n; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k)
+                    acc = std::fma(src[(o * n + k) * inner + i], dm[(size_t)j * n + k], acc);
+                dst[(o * n + j) * inner + i] = acc;
+            }
+}
+
+static void put(std::vector<unsigned char> &out, const void *p, size_t bytes) {
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    out.insert(out.end(), b, b + bytes);
+}
+
+// _binary.py:157-185 (header) + :208-236 / :289-346 (bodies); little-endian host assumed (x86-64)
+static std::vector<unsigned char> serialize_pcb(const PcbFile &pf) {
+    std::vector<unsigned char> out;
+    const unsigned char head[12] = {'P', 'C', 'B', 0, 1, 0, (unsigned char)pf.kind, 0, 0, 0, 0, 0};
+    put(out, head, 12);
+    const uint32_t D = (uint32_t)pf.D;
+    put(out, &D, 4);
+    put(out, pf.lo.data(), 8 * (size_t)pf.D);
+    put(out, pf.hi.data(), 8 * (size_t)pf.D);
+    for (int d = 0; d < pf.D; ++d) {
+        const uint32_t v = (uint32_t)pf.n[d];
+        put(out, &v, 4);
+    }
+    if (pf.kind == 2) {
+        for (int d = 0; d < pf.D; ++d) {
+            const uint32_t v = (uint32_t)pf.num_knots[d];
+            put(out, &v, 4);
+        }
+        put(out, pf.knots.data(), 8 * pf.knots.size());
+        const uint32_t P = (uint32_t)pf.P;
+        put(out, &P, 4);
+    }
+    put(out, pf.values.data(), 8 * pf.values.size());
+    return out;
+}
+
+static int write_file(const char *path, const std::vector<unsigned char> &raw) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(PCB_EINVAL, "cannot open %s for writing", path);
+    const size_t done = fwrite(raw.data(), 1, raw.size(), f);
+    if (fclose(f) != 0 || done != raw.size()) return fail(PCB_EINVAL, "short write to %s", path);
+    return PCB_OK;
+}
+
+static int check_grid(int D, const double *lo, const double *hi, const int32_t *n) {
+    PCB_REQUIRE(D >= 1 && D <= 64, "num_dimensions must be >= 1, got %d", D);
+    for (int d = 0; d < D; ++d) {
+        PCB_REQUIRE(lo[d] < hi[d], "domain[%d]: lo (%g) must be < hi (%g)", d, lo[d], hi[d]);
+        PCB_REQUIRE(n[d] >= 1, "n_nodes[%d] must be >= 1, got %d", d, n[d]);
+    }
+    return PCB_OK;
+}
+
 }  // namespace pcb
 
 using namespace pcb;
 
+// ---- native writer (reference _binary.py:208-236, 289-346): byte-identical files -----------------------
+extern "C" PCB_API int pcb_file_write_approx(const char *path, int D, const double *lo, const double *hi,
+                                             const int32_t *n, const double *tensor) {
+    PCB_REQUIRE(path && lo && hi && n && tensor, "null argument");
+    if (int rc = check_grid(D, lo, hi, n)) return rc;
+    try {
+        PcbFile pf;
+        pf.kind = 1;
+        pf.D = D;
+        pf.lo.assign(lo, lo + D);
+        pf.hi.assign(hi, hi + D);
+        pf.n.assign(n, n + D);
+        size_t per = 1;
+        for (int d = 0; d < D; ++d) per *= (size_t)n[d];
+        for (size_t i = 0; i < per; ++i)
+            if (!std::isfinite(tensor[i])) return fail(PCB_EINVAL, "tensor_values contains NaN or Inf");
+        pf.values.assign(tensor, tensor + per);
+        return write_file(path, serialize_pcb(pf));
+    } catch (const std::bad_alloc &) {
+        return fail(PCB_ENOMEM, "out of host memory while writing %s", path);
+    }
+}
+
+extern "C" PCB_API int pcb_file_write_spline(const char *path, int D, const double *lo, const double *hi,
+                                             const int32_t *n, const int32_t *num_knots,
+                                             const double *knots_cat, int P,
+                                             const double *const *piece_tensors) {
+    PCB_REQUIRE(path && lo && hi && n && num_knots && piece_tensors, "null argument");
+    if (int rc = check_grid(D, lo, hi, n)) return rc;
+    try {
+        PcbFile pf;
+        pf.kind = 2;
+        pf.D = D;
+        pf.lo.assign(lo, lo + D);
+        pf.hi.assign(hi, hi + D);
+        pf.n.assign(n, n + D);
+        pf.num_knots.assign(num_knots, num_knots + D);
+        size_t total = 0;
+        long long expect = 1;
+        for (int d = 0; d < D; ++d) {
+            PCB_REQUIRE(num_knots[d] >= 0, "num_knots[%d] must be >= 0", d);
+            total += (size_t)num_knots[d];
+            expect *= (long long)num_knots[d] + 1;
+        }
+        PCB_REQUIRE(total == 0 || knots_cat, "null knots");
+        PCB_REQUIRE((long long)P == expect, "num_pieces=%d does not match prod(num_knots+1)=%lld", P, expect);
+        if (total) pf.knots.assign(knots_cat, knots_cat + total);
+        pf.P = P;
+        size_t per = 1;
+        for (int d = 0; d < D; ++d) per *= (size_t)n[d];
+        pf.values.reserve(per * (size_t)P);
+        for (int p = 0; p < P; ++p) {
+            PCB_REQUIRE(piece_tensors[p], "Cannot save an unbuilt ChebyshevSpline");
+            pf.values.insert(pf.values.end(), piece_tensors[p], piece_tensors[p] + per);
+        }
+        return write_file(path, serialize_pcb(pf));
+    } catch (const std::bad_alloc &) {
+        return fail(PCB_ENOMEM, "out of host memory while writing %s", path);
+    }
+}
+
+// bytes -> parsed file -> bytes: the native reader and writer composed (round-trip identity)
+extern "C" PCB_API int pcb_file_rewrite(const char *in_path, const char *out_path) {
+    PCB_REQUIRE(in_path && out_path, "null argument");
+    try {
+        PcbFile pf;
+        if (int rc = parse_pcb(in_path, &pf)) return rc;
+        return write_file(out_path, serialize_pcb(pf));
+    } catch (const std::bad_alloc &) {
+        return fail(PCB_ENOMEM, "out of host memory while rewriting %s", in_path);
+    }
+}
+
+// The grid arrays the native loader derives from (lo, hi, n): nodes, barycentric weights and the
+// differentiation matrix (n x n), exposed so tests can compare them with the NumPy recipes.
+extern "C" PCB_API int pcb_file_grid_arrays(double lo, double hi, int n, double *nodes, double *weights,
+                                            double *dmat) {
+    PCB_REQUIRE(nodes && weights && n >= 1 && lo < hi, "bad grid description");
+    make_nodes(lo, hi, n, nodes);
+    make_weights(nodes, n, weights);
+    if (dmat) make_diff_matrix(nodes, weights, n, dmat);
+    return PCB_OK;
+}
+
 // kind: 1 = ChebyshevApproximation, 2 = ChebyshevSpline
-static int plan_from_file(int dev, const char *path, void **plan, int *kind, int *D);
+static int plan_from_file(int dev, const char *path, int G, const int32_t *orders, void **plan,
+                          int *kind, int *D);
 
 extern "C" PCB_API int pcb_plan_from_file(int dev, const char *path, void **plan, int *kind, int *D) {
+    return pcb_plan_from_file_orders(dev, path, 0, nullptr, plan, kind, D);
+}
+
+// G derivative-order rows (G x D, HOST) -> plan with G outputs per query; G = 0: values only.
+extern "C" PCB_API int pcb_plan_from_file_orders(int dev, const char *path, int G, const int32_t *orders,
+                                                 void **plan, int *kind, int *D) {
     try {  // no C++ exception may cross the C ABI
-        return plan_from_file(dev, path, plan, kind, D);
+        return plan_from_file(dev, path, G, orders, plan, kind, D);
     } catch (const std::bad_alloc &) {
         return fail(PCB_ENOMEM, "out of host memory while loading %s", path ? path : "(null)");
     } catch (const std::exception &e) {
@@ -158,10 +346,19 @@ extern "C" PCB_API int pcb_plan_from_file(int dev, const char *path, void **plan
     }
 }
 
-static int plan_from_file(int dev, const char *path, void **plan, int *kind, int *D) {
+static int plan_from_file(int dev, const char *path, int G, const int32_t *orders, void **plan,
+                          int *kind, int *D) {
     PCB_REQUIRE(path && plan, "null argument");
+    PCB_REQUIRE(G >= 0 && G <= 64 && (G == 0 || orders), "bad derivative rows");
     PcbFile pf;
     if (int rc = parse_pcb(path, &pf)) return rc;
+    std::vector<int32_t> value_row((size_t)pf.D, 0);
+    if (G == 0) {
+        G = 1;
+        orders = value_row.data();
+    }
+    for (int i = 0; i < G * pf.D; ++i)
+        PCB_REQUIRE(orders[i] >= 0 && orders[i] <= 8, "derivative order %d outside [0, 8]", orders[i]);
     if (kind) *kind = pf.kind;
     if (D) *D = pf.D;
     size_t per = 1;
@@ -178,13 +375,27 @@ static int plan_from_file(int dev, const char *path, void **plan, int *kind, int
             make_weights(nodes.data() + off, pf.n[d], weights.data() + off);
             off += pf.n[d];
         }
-        const double *tensor = pf.values.data();
-        return pcb_full_plan_create(dev, pf.D, pf.n.data(), nodes.data(), weights.data(), 1, &tensor, plan);
+        // differentiation matrices natively, derivative tensors on the device (N3)
+        std::vector<double> dms;
+        off = 0;
+        for (int d = 0; d < pf.D; ++d) {
+            const size_t at = dms.size();
+            dms.resize(at + (size_t)pf.n[d] * pf.n[d]);
+            make_diff_matrix(nodes.data() + off, weights.data() + off, pf.n[d], dms.data() + at);
+            off += pf.n[d];
+        }
+        bool small_n = true;
+        for (int d = 0; d < pf.D; ++d) small_n = small_n && pf.n[d] <= 64;
+        PCB_REQUIRE(small_n, "n_nodes above 64 are not supported by the native loader");
+        return pcb_full_plan_create_from_values(dev, pf.D, pf.n.data(), nodes.data(), weights.data(),
+                                                dms.data(), pf.values.data(), G, orders, plan);
     }
     // spline: pieces in C-order over the per-dimension interval indices, flat n_nodes
     std::vector<int32_t> piece_n((size_t)pf.P * pf.D);
     std::vector<double> nodes((size_t)pf.P * sum_n), weights((size_t)pf.P * sum_n);
-    std::vector<const double *> tensors(pf.P);
+    std::vector<const double *> tensors((size_t)pf.P * G);
+    std::vector<std::vector<double>> derived;  // derivative tensors of the pieces (host, small)
+    derived.reserve((size_t)pf.P * G);
     std::vector<int> idx(pf.D, 0);
     std::vector<size_t> koff(pf.D, 0);
     for (int d = 1; d < pf.D; ++d) koff[d] = koff[d - 1] + pf.num_knots[d - 1];
@@ -199,14 +410,35 @@ static int plan_from_file(int dev, const char *path, void **plan, int *kind, int
             make_weights(nd, pf.n[d], weights.data() + (size_t)p * sum_n + off);
             off += pf.n[d];
         }
-        tensors[p] = pf.values.data() + (size_t)p * per;
+        const double *value_t = pf.values.data() + (size_t)p * per;
+        for (int g = 0; g < G; ++g) {
+            const int32_t *o = orders + (size_t)g * pf.D;
+            const double *cur = value_t;
+            int poff = sum_n;
+            for (int d = pf.D - 1; d >= 0; --d) {  // _apply_derivative_passes: d = D-1 .. 0
+                poff -= pf.n[d];
+                if (o[d] == 0) continue;
+                std::vector<double> dm((size_t)pf.n[d] * pf.n[d]);
+                make_diff_matrix(nodes.data() + (size_t)p * sum_n + poff,
+                                 weights.data() + (size_t)p * sum_n + poff, pf.n[d], dm.data());
+                long long outer = 1, inner = 1;
+                for (int e = 0; e < d; ++e) outer *= pf.n[e];
+                for (int e = d + 1; e < pf.D; ++e) inner *= pf.n[e];
+                for (int rep = 0; rep < o[d]; ++rep) {
+                    derived.emplace_back(per);
+                    host_deriv_pass(cur, derived.back().data(), outer, pf.n[d], inner, dm.data());
+                    cur = derived.back().data();
+                }
+            }
+            tensors[(size_t)p * G + g] = cur;
+        }
         for (int d = pf.D - 1; d >= 0; --d) {  // C-order increment
             if (++idx[d] <= pf.num_knots[d]) break;
             idx[d] = 0;
         }
     }
     return pcb_spline_plan_create(dev, pf.D, pf.num_knots.data(), pf.knots.empty() ? nullptr : pf.knots.data(),
-                                  pf.P, piece_n.data(), nodes.data(), weights.data(), 1, tensors.data(),
+                                  pf.P, piece_n.data(), nodes.data(), weights.data(), G, tensors.data(),
                                   plan);
 }
 

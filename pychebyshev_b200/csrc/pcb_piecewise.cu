@@ -52,8 +52,12 @@ struct SplinePlan : PlanBase {
     bool bank_ok = false;
     std::vector<BankPart> parts;
     size_t bank_smem = 0;
+    // 2-D splines on the FP64 tensor cores: piece tensors in MMA fragment order [piece][output]
+    bool dmma2d_ok = false;
+    double *d_frags = nullptr;
     ~SplinePlan() override;
     void free_all() {
+        if (d_frags) cudaFree(d_frags);
         if (d_num_knots) cudaFree(d_num_knots);
         if (d_knots) cudaFree(d_knots);
         if (d_desc) cudaFree(d_desc);
@@ -77,8 +81,15 @@ struct SliderPlan : PlanBase {
     std::vector<double> h_bank;
     std::vector<BankGrid> h_desc;
     size_t bank_smem = 0;
+    // sliders of 2-D slides on the FP64 tensor cores: slide tensors in MMA fragment order
+    bool dmma2d_ok = false;
+    double *d_frags = nullptr;
+    int *d_frag_off = nullptr;
+    int nfrag = 0;
     ~SliderPlan() override;
     void free_all() {
+        if (d_frags) cudaFree(d_frags);
+        if (d_frag_off) cudaFree(d_frag_off);
         if (d_desc) cudaFree(d_desc);
         if (d_ints) cudaFree(d_ints);
         if (d_nodes) cudaFree(d_nodes);
@@ -548,6 +559,252 @@ slider_bank_kernel(int D, int S, int G, double pivot, const int *__restrict__ ou
         if (live && g < G) o[g] = acc[g];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 2-D grids on the FP64 tensor cores (round 2).  A 2-D barycentric value is the bilinear form
+//     p(x, y) = a(x)^T T b(y) / (sum a * sum b)
+// so for 8 queries at a time the contraction over the FIRST axis is an 8 x n0 by n0 x n1 GEMM:
+//     U[q, j] = sum_i A[q, i] T[i, j]           mma.sync.m8n8k4.f64  (SASS DMMA.8x8x4)
+// followed by a per-query dot with b(y): 2 products per lane and a quad shuffle.  One DMMA does the
+// work of 8 DFMA warp instructions, which is what the thread-per-query evaluator was short of: ncu
+// on spline_bank_kernel<1,2> showed FP64 pipe 25 %, issue slots 41 % busy, 1790 instructions per
+// query against ~600 FP64 ones.  Here a warp owns 32 queries:
+//   1. every lane builds the two weight rows of ITS query in registers (product form, operands on
+//      the uniform datapath from the constant bank, exactly as in the bank kernels) and parks them
+//      in a per-warp shared tile, i-major with padded strides (36 / 34 doubles) so that both the
+//      stores and the fragment loads below are bank-conflict free;
+//   2. for each of the 4 row tiles (8 queries) and each piece present in it: A fragments from the
+//      tile, B fragments = the piece's tensor pre-arranged in fragment order (staged in shared
+//      memory once per CTA), ceil(n0/4) x ceil(n1/8) DMMAs, the fold with b, a quad reduction;
+//   3. the owner lane scales by 1 / (sum a * sum b) and stores.
+// Splines first counting-sort the CTA's queries by piece (as spline_bank_kernel does), so all but
+// <= P - 1 row tiles per CTA are single-piece.  Sliders run the three steps once per slide.
+// ---------------------------------------------------------------------------------------------
+constexpr int BL_THREADS = 128;                 // 4 warps; ~10 KB of tiles per warp
+constexpr int BL_SA = 36, BL_SB = 34;           // padded strides (doubles) of the weight tiles
+constexpr int BL_FRAG = 256;                    // doubles per (grid, output): 4 k-blocks x 2 n-tiles x 32 lanes
+constexpr int BL_MAX_FRAGS = 24;                // staged in shared memory (48 KB)
+constexpr int BL_OUT = 4;                       // outputs folded per pass
+constexpr int BL_WARP_DOUBLES = 16 * BL_SA + 16 * BL_SB + BL_OUT * 32;
+
+__device__ __forceinline__ void bl_dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// Weight rows of bank grid `g` for this lane's query into the warp tile (predicated on `keep`);
+// returns 1 / (sum a * sum b) (1-D factors folded) for the lanes that keep it.
+template <typename Coord>
+__device__ __forceinline__ double bl_rows(const BankGrid &g, Coord x, bool keep, double *sA, double *sB,
+                                          int lane) {
+    double row[GRID_NL];
+    const double sa = bank_row<false>(x(0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
+                                      __double_as_longlong(c_grid[g.scale_off + 2 + 0]), row, nullptr, 0, 1.0);
+    if (keep) {
+#pragma unroll
+        for (int i = 0; i < GRID_NL; ++i) sA[i * BL_SA + lane] = row[i];
+    }
+    const double sb = bank_row<false>(x(1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
+                                      g.weight_off + g.n[0],
+                                      __double_as_longlong(c_grid[g.scale_off + 2 + 1]), row, nullptr, 0, 1.0);
+    if (keep) {
+#pragma unroll
+        for (int j = 0; j < GRID_NL; ++j) sB[j * BL_SB + lane] = row[j];
+    }
+    return bank_rcp(sa * sb);
+}
+
+// Row tile t (queries 8t..8t+7 of the warp) against grid `g`, outputs [o0, o0 + no): the lanes
+// with (lane & 3) == 0 whose row passes `take` write sOut[o * 32 + row].
+__device__ __forceinline__ void bl_tile(const BankGrid &g, const double *frag, int o0, int no, int t,
+                                        const double *sA, const double *sB, double *sOut, int lane,
+                                        bool take) {
+    const int r = lane >> 2, c = lane & 3;
+    const int KB = (g.n[0] + 3) >> 2, NT = (g.n[1] + 7) >> 3;
+    double af[4];
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) af[kb] = kb < KB ? sA[(4 * kb + c) * BL_SA + 8 * t + r] : 0.0;
+    double bq[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            bq[nt][e] = nt < NT ? sB[(8 * nt + 2 * c + e) * BL_SB + 8 * t + r] : 0.0;
+    for (int o = 0; o < no; ++o) {
+        const double *f = frag + (size_t)(o0 + o) * BL_FRAG + lane;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            if (kb < KB) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+                    if (nt < NT) bl_dmma(acc[nt][0], acc[nt][1], af[kb], f[(kb * 2 + nt) * 32]);
+            }
+        }
+        double part = acc[0][0] * bq[0][0];
+        part = fma(acc[0][1], bq[0][1], part);
+        part = fma(acc[1][0], bq[1][0], part);
+        part = fma(acc[1][1], bq[1][1], part);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (c == 0 && take) sOut[o * 32 + 8 * t + r] = part;
+    }
+}
+
+__device__ __forceinline__ void bl_stage_frags(double *sFrag, const double *__restrict__ frags, int nfrag) {
+    for (int e = threadIdx.x; e < nfrag * BL_FRAG; e += BL_THREADS) sFrag[e] = __ldg(frags + e);
+}
+
+__global__ void __launch_bounds__(BL_THREADS, 4)
+spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
+                     const double *__restrict__ knots, const double *__restrict__ frags,
+                     const double *__restrict__ pts, int64_t N, double *__restrict__ out,
+                     int32_t *__restrict__ piece_out) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_cnt[BANK_GRIDS];
+    __shared__ unsigned short s_perm[BL_THREADS];
+    __shared__ unsigned char s_piece[BL_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *sFrag = smem;
+    double *sA = smem + (size_t)P * G * BL_FRAG + warp * BL_WARP_DOUBLES;
+    double *sB = sA + 16 * BL_SA;
+    double *sOut = sB + 16 * BL_SB;
+    const int64_t q0 = (int64_t)blockIdx.x * BL_THREADS;
+    bl_stage_frags(sFrag, frags, P * G);
+    int mine;
+    {
+        const int64_t ql = q0 + tid < N ? q0 + tid : N - 1;
+        mine = spline_piece_index(2, num_knots, knot_off, knots, pts + ql * 2);
+        if (piece_out && q0 + tid < N) piece_out[q0 + tid] = mine;
+    }
+    // counting sort of the CTA's queries by piece (see spline_bank_kernel)
+    if (tid < BANK_GRIDS) s_cnt[tid] = 0;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, mine);
+    const int leader = __ffs(peers) - 1;
+    int warp_off = 0;
+    if (lane == leader) warp_off = atomicAdd(&s_cnt[mine], __popc(peers));
+    warp_off = __shfl_sync(0xffffffffu, warp_off, leader);
+    __syncthreads();
+    int pos = warp_off + __popc(peers & ((1u << lane) - 1u));
+    for (int p = 0; p < P; ++p) pos += p < mine ? s_cnt[p] : 0;
+    s_perm[pos] = (unsigned short)tid;
+    s_piece[pos] = (unsigned char)mine;
+    __syncthreads();  // also: fragments staged
+    mine = s_piece[tid];
+    const int64_t q = q0 + s_perm[tid];
+    const bool live = q < N;
+    const double *x = pts + (live ? q : N - 1) * 2;
+    double *o = out + (live ? q : N - 1) * G;
+    // 1. weight rows, once per piece present in the warp (uniform loop, predicated stores)
+    const unsigned present = __reduce_or_sync(0xffffffffu, 1u << mine);
+    double inv = 1.0;
+    for (int p = 0; p < P; ++p) {
+        if (!((present >> p) & 1u)) continue;
+        const double v = bl_rows(c_bgrid[p], [&](int d) { return __ldg(x + d); }, mine == p, sA, sB, lane);
+        if (mine == p) inv = v;
+    }
+    __syncwarp();
+    // 2. + 3. row tiles x pieces present in the tile, BL_OUT outputs per pass
+    for (int o0 = 0; o0 < G; o0 += BL_OUT) {
+        const int no = G - o0 < BL_OUT ? G - o0 : BL_OUT;
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+            const int prow = __shfl_sync(0xffffffffu, mine, 8 * t + (lane >> 2));
+            const unsigned here = __reduce_or_sync(0xffffffffu, 1u << prow);
+            for (int p = 0; p < P; ++p) {
+                if (!((here >> p) & 1u)) continue;
+                bl_tile(c_bgrid[p], sFrag + (size_t)p * G * BL_FRAG, o0, no, t, sA, sB, sOut, lane,
+                        prow == p);
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < no; ++k) {
+            const double v = sOut[k * 32 + lane] * inv;
+            if (live) o[o0 + k] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// Slider of 2-D slides: value rows accumulate pivot + sum_s (slide_s - pivot) left to right
+// (slider.py:310-318), a derivative row takes its slide's output, cross-slide rows are exactly 0.
+__global__ void __launch_bounds__(BL_THREADS, 4)
+slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ out_slide,
+                     const int *__restrict__ row_out, const int *__restrict__ frag_off, int nfrag,
+                     const double *__restrict__ frags, const double *__restrict__ pts, int64_t N,
+                     double *__restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *sFrag = smem;
+    double *sA = smem + (size_t)nfrag * BL_FRAG + warp * BL_WARP_DOUBLES;
+    double *sB = sA + 16 * BL_SA;
+    double *sOut = sB + 16 * BL_SB;
+    const int64_t q = (int64_t)blockIdx.x * BL_THREADS + tid;
+    const bool live = q < N;
+    const double *x = pts + (live ? q : N - 1) * D;
+    double *o = out + (live ? q : N - 1) * G;
+    bl_stage_frags(sFrag, frags, nfrag);
+    double acc[SLIDER_ACC];
+#pragma unroll
+    for (int g = 0; g < SLIDER_ACC; ++g) acc[g] = (g < G && out_slide[g] == -1) ? pivot : 0.0;
+    for (int g = SLIDER_ACC; g < G; ++g)
+        if (live) o[g] = out_slide[g] == -1 ? pivot : 0.0;
+    __syncthreads();
+    for (int s = 0; s < S; ++s) {
+        const BankGrid &gr = c_bgrid[s];
+        const int sg = gr.outputs;
+        if (sg == 0) continue;
+        const double inv = bl_rows(gr, [&](int d) { return __ldg(x + gr.dims[d]); }, true, sA, sB, lane);
+        __syncwarp();
+        for (int o0 = 0; o0 < sg; o0 += BL_OUT) {
+            const int no = sg - o0 < BL_OUT ? sg - o0 : BL_OUT;
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t)
+                bl_tile(gr, sFrag + (size_t)frag_off[s] * BL_FRAG, o0, no, t, sA, sB, sOut, lane, true);
+            __syncwarp();
+            for (int k = 0; k < no; ++k) {
+                const int so = o0 + k;
+                const double r = sOut[k * 32 + lane] * inv;
+#pragma unroll
+                for (int g = 0; g < SLIDER_ACC; ++g) {
+                    if (g < G) {
+                        const int os = out_slide[g], ro = row_out[g];
+                        if (os == s && ro == so)
+                            acc[g] = r;
+                        else if (os == -1 && so == 0 && ro == 0)
+                            acc[g] = acc[g] + (r - pivot);
+                    }
+                }
+                for (int g = SLIDER_ACC; g < G; ++g) {
+                    const int os = out_slide[g], ro = row_out[g];
+                    if (live) {
+                        if (os == s && ro == so)
+                            o[g] = r;
+                        else if (os == -1 && so == 0 && ro == 0)
+                            o[g] = o[g] + (r - pivot);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < SLIDER_ACC; ++g)
+        if (live && g < G) o[g] = acc[g];
+}
+
+// Fragment image of one n0 x n1 tensor: f[(kb * 2 + nt) * 32 + lane] = T[4 kb + lane % 4][8 nt + lane / 4]
+static void bl_make_frag(const double *t, int n0, int n1, double *f) {
+    for (int kb = 0; kb < 4; ++kb)
+        for (int nt = 0; nt < 2; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int i = 4 * kb + lane % 4, j = 8 * nt + lane / 4;
+                f[(kb * 2 + nt) * 32 + lane] = (i < n0 && j < n1) ? t[(size_t)i * n1 + j] : 0.0;
+            }
+}
+
 // Bank image of a set of grids: [tensors (already interleaved, GridDesc.tensor_off) | nodes |
 // weights].  Returns false when the plan does not qualify for the bank path.
 static bool bank_build(const std::vector<GridDesc> &desc, const std::vector<double> &il,
@@ -622,9 +879,9 @@ static bool bank_build(const std::vector<GridDesc> &desc, const std::vector<doub
 
 static int bank_launch(const PlanBase *pl, uint64_t plan_id, const std::vector<double> &h_bank,
                        const std::vector<BankGrid> &h_desc, const void *kernel, void **args,
-                       size_t smem, int64_t N, cudaStream_t st) {
+                       size_t smem, int64_t N, cudaStream_t st, int threads = BANK_THREADS) {
     PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
-    const int64_t blocks = (N + BANK_THREADS - 1) / BANK_THREADS;
+    const int64_t blocks = (N + threads - 1) / threads;
     PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
     const int rc = g_grid_bank.acquire(pl->dev, plan_id, st, [&](cudaStream_t s) {
         cudaError_t e = cudaMemcpyToSymbolAsync(c_grid, h_bank.data(), h_bank.size() * sizeof(double), 0,
@@ -634,7 +891,7 @@ static int bank_launch(const PlanBase *pl, uint64_t plan_id, const std::vector<d
                                        cudaMemcpyHostToDevice, s);
     });
     if (rc) return rc;
-    const cudaError_t e = cudaLaunchKernel(kernel, dim3((unsigned)blocks), dim3(BANK_THREADS), args, smem, st);
+    const cudaError_t e = cudaLaunchKernel(kernel, dim3((unsigned)blocks), dim3(threads), args, smem, st);
     g_grid_bank.release(pl->dev, st);
     g_launches.fetch_add(1);
     PCB_CUDA(e);
@@ -793,6 +1050,20 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
         delete pl;
         return fail(PCB_ECUDA, "device allocation/upload for the spline plan failed");
     }
+    // 2-D pieces of at most 16 x 16 nodes: tensor-core path (nodes / weights from the bank image)
+    if (D == 2 && pl->bank_ok && P <= BANK_GRIDS && P * G <= BL_MAX_FRAGS && !getenv("PCB_NO_DMMA2D")) {
+        bool fits = true;
+        for (int p = 0; p < P; ++p) fits = fits && desc[p].n[0] <= 16 && desc[p].n[1] <= 16;
+        if (fits) {
+            std::vector<double> fr((size_t)P * G * BL_FRAG);
+            for (int p = 0; p < P; ++p)
+                for (int g = 0; g < G; ++g)
+                    bl_make_frag(piece_tensors_host[(size_t)p * G + g], desc[p].n[0], desc[p].n[1],
+                                 fr.data() + ((size_t)p * G + g) * BL_FRAG);
+            pl->dmma2d_ok = upload(&pl->d_frags, fr.data(), fr.size());
+            if (!pl->dmma2d_ok) cudaGetLastError();
+        }
+    }
     *plan = pl;
     return PCB_OK;
 }
@@ -826,6 +1097,15 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
     if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    if (pl->dmma2d_ok) {
+        const SplinePlan::BankPart &part = pl->parts[0];  // nodes / weights / scales are in every image
+        const size_t dsm = ((size_t)pl->P * pl->G * BL_FRAG + (BL_THREADS / 32) * BL_WARP_DOUBLES) * sizeof(double);
+        void *dargs[] = {(void *)&pl->G, (void *)&pl->P, (void *)&pl->d_num_knots, (void *)&pl->d_knot_off,
+                         (void *)&pl->d_knots, (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
+                         (void *)&d_out, (void *)&d_piece};
+        return bank_launch(pl, part.id, part.h_bank, part.h_desc, (const void *)spline2d_dmma_kernel, dargs,
+                           dsm, N, static_cast<cudaStream_t>(stream), BL_THREADS);
+    }
     if (pl->bank_ok) {
         for (const SplinePlan::BankPart &part : pl->parts) {
             const void *uk = BANK_KERNEL_TABLE(spline_bank_kernel, part.GB, grid_pick_dm(pl->D));
@@ -984,6 +1264,29 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
         delete pl;
         return fail(PCB_ECUDA, "device allocation/upload for the slider plan failed");
     }
+    // all slides 2-D with at most 16 x 16 nodes: tensor-core path
+    if (pl->bank_ok && S <= BANK_GRIDS && !getenv("PCB_NO_DMMA2D")) {
+        bool fits = true;
+        int nfrag = 0;
+        std::vector<int> foff(S, 0);
+        for (int sl = 0; sl < S; ++sl) {
+            fits = fits && desc[sl].D == 2 && desc[sl].n[0] <= 16 && desc[sl].n[1] <= 16;
+            foff[sl] = nfrag;
+            nfrag += slide_G[sl];
+        }
+        if (fits && nfrag >= 1 && nfrag <= BL_MAX_FRAGS) {
+            std::vector<double> fr((size_t)nfrag * BL_FRAG, 0.0);
+            for (int sl = 0; sl < S; ++sl)
+                for (int k = 0; k < slide_G[sl]; ++k)
+                    if (outs[sl][k])
+                        bl_make_frag(outs[sl][k], desc[sl].n[0], desc[sl].n[1],
+                                     fr.data() + (size_t)(foff[sl] + k) * BL_FRAG);
+            pl->nfrag = nfrag;
+            pl->dmma2d_ok = upload(&pl->d_frags, fr.data(), fr.size()) &&
+                            upload(&pl->d_frag_off, foff.data(), foff.size());
+            if (!pl->dmma2d_ok) cudaGetLastError();
+        }
+    }
     *plan = pl;
     return PCB_OK;
 }
@@ -999,6 +1302,15 @@ extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64
     const size_t smem = (size_t)pl->max_sum_n * PW_THREADS * sizeof(double);
     if (!pl->bank_ok && smem > (size_t)pl->smem_optin)
         return fail(PCB_EUNSUPPORTED, "weight rows of %d nodes do not fit in shared memory", pl->max_sum_n);
+    if (pl->dmma2d_ok) {
+        const size_t dsm = ((size_t)pl->nfrag * BL_FRAG + (BL_THREADS / 32) * BL_WARP_DOUBLES) * sizeof(double);
+        void *dargs[] = {(void *)&pl->D, (void *)&pl->S, (void *)&pl->G, (void *)&pl->pivot,
+                         (void *)&pl->d_out_slide, (void *)&pl->d_row_out, (void *)&pl->d_frag_off,
+                         (void *)&pl->nfrag, (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
+                         (void *)&d_out};
+        return bank_launch(pl, pl->plan_id, pl->h_bank, pl->h_desc, (const void *)slider2d_dmma_kernel, dargs,
+                           dsm, N, static_cast<cudaStream_t>(stream), BL_THREADS);
+    }
     if (pl->bank_ok) {
         const void *uk = BANK_KERNEL_TABLE(slider_bank_kernel, pl->GB, grid_pick_dm(pl->max_D));
         void *uargs[] = {(void *)&pl->D, (void *)&pl->S, (void *)&pl->G, (void *)&pl->pivot,

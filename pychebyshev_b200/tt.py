@@ -338,6 +338,62 @@ class ChebyshevTT:
         pts = np.asarray([list(point)], dtype=np.float64)
         return [float(v) for v in self.eval_multi_batch(pts, derivative_orders)[0]]
 
+    # ------------------------------------------------------------------ grid evaluation (N4)
+    def grid_nodes(self) -> List[np.ndarray]:
+        """Chebyshev nodes per USER dimension (ascending), the grid the cores interpolate on."""
+        self._check_built()
+        out = [None] * self.num_dimensions
+        for k, u in enumerate(self._dim_order):
+            lo, hi = self.domain[k]
+            out[u] = _grid.cheb_nodes(float(lo), float(hi), int(self.n_nodes[k]))
+        return out
+
+    def eval_grid_indices(self, indices, *, device=None):
+        """Values at grid multi-indices ``(M, D)`` (user frame) in ONE launch of the chain kernel.
+
+        The batched twin of the per-index ``_eval_tt`` of the reference's TT-Cross
+        (``tensor_train.py:223-228``, used for its cross-matrix index sets ``:287-297`` and its
+        convergence check ``:321-330``): the node coordinates are gathered on the device and go
+        through ``pcb_tt_eval``.  Returns a NumPy array for NumPy input, a CUDA tensor otherwise.
+        """
+        import torch
+
+        self._check_built()
+        plan = self._plan(device)
+        as_numpy = not isinstance(indices, torch.Tensor)
+        idx = torch.as_tensor(np.asarray(indices) if as_numpy else indices)
+        if idx.dim() != 2 or idx.shape[1] != self.num_dimensions:
+            raise ValueError(f"indices must have shape (M, {self.num_dimensions})")
+        dev = torch.device("cuda", plan.dev)
+        idx = idx.to(device=dev, dtype=torch.int64)
+        nodes = self.grid_nodes()
+        for u, x in enumerate(nodes):
+            if idx.shape[0] and (int(idx[:, u].min()) < 0 or int(idx[:, u].max()) >= len(x)):
+                raise IndexError(f"grid index out of range in dimension {u}")
+        with torch.cuda.device(dev):
+            pts = torch.stack([torch.from_numpy(x).to(dev)[idx[:, u]] for u, x in enumerate(nodes)],
+                              dim=1).contiguous()
+            vals = plan.eval_device(pts)[:, 0]
+        return vals.cpu().numpy() if as_numpy else vals
+
+    def to_dense(self, *, device=None, as_numpy: bool = True):
+        """The full tensor of node values, axes in user-frame order (reference
+        ``tensor_train.py:1874-1917``), by evaluating the chain kernel at every grid node -- the
+        node grid is generated on the device, so only the result crosses PCIe."""
+        import torch
+
+        self._check_built()
+        plan = self._plan(device)
+        dev = torch.device("cuda", plan.dev)
+        nodes = self.grid_nodes()
+        with torch.cuda.device(dev):
+            axes = [torch.from_numpy(x).to(dev) for x in nodes]
+            mesh = torch.meshgrid(*axes, indexing="ij")
+            pts = torch.stack([m.reshape(-1) for m in mesh], dim=1).contiguous()
+            del mesh
+            vals = plan.eval_device(pts)[:, 0].reshape([len(x) for x in nodes])
+        return vals.cpu().numpy() if as_numpy else vals
+
     # ------------------------------------------------------------------ persistence
     def save(self, path) -> None:
         """Pickle (the reference has no ``.pcb`` layout for tensor trains)."""

@@ -13,18 +13,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-_before = 0
+# at plugin IMPORT time (before pytest imports the reference's conftest.py, which does
+# `from pychebyshev import ...`): put the unmodified reference on sys.path and swap the backend in
+from oracle import reference as _R  # noqa: E402
 
+_ref = _R.load()
+from pychebyshev_b200 import _engine as _eng, dropin as _dropin  # noqa: E402
 
-def pytest_configure(config):
-    global _before
-    from oracle import reference as R
-
-    ref = R.load()
-    from pychebyshev_b200 import _engine, dropin
-
-    dropin.install(ref)
-    _before = _engine.launch_count()
+_dropin.install(_ref)
+_before = _eng.launch_count()
 
 
 def pytest_terminal_summary(terminalreporter):

@@ -221,3 +221,41 @@ def test_install_rebinds_reference_methods_and_uninstall_restores_them():
         dropin.uninstall()
     assert ref.ChebyshevTT.eval_batch is orig and not dropin.installed()
     assert np.array_equal(tt.eval_batch(pts5), cpu_tt)
+
+
+# ------------------------------------------------------------------------------------------
+# N4: TT build-side evaluation through the chain kernel
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["tt_bs5d", "tt_4d_perm"])
+def test_n4_to_dense_and_grid_index_sets_side_by_side(name):
+    """``to_dense`` (tensor_train.py:1874-1917) and batched evaluation at grid multi-indices (the
+    TT-Cross index sets / convergence check, :223-228, :287-297, :321-330) on the device against the
+    reference's own ``to_dense`` on this box."""
+    _ref()
+    from oracle import ref_objects as RO
+    from pychebyshev_b200 import dropin
+
+    g = G.load(name)
+    cores, domain, dim_order = G.tt_parts(g)
+    tt = RO.tt_from_cores(cores, domain, dim_order)
+    mirror = dropin.adopt(tt)
+    ref = tt.to_dense()
+    got = mirror.to_dense()
+    assert got.shape == ref.shape
+    scale_close(got.ravel(), ref.ravel(), f"{name} to_dense")
+    rng = np.random.default_rng(SEED + 8)
+    idx = np.column_stack([rng.integers(0, n, size=5000) for n in ref.shape])
+    vals = mirror.eval_grid_indices(idx)
+    scale_close(vals, ref[tuple(idx.T)], f"{name} grid index sets")
+    # a cross-matrix index set of the reference's TT-Cross: left x node x right (C-order rows)
+    D = len(ref.shape)
+    k = D // 2
+    left = np.column_stack([rng.integers(0, ref.shape[d], size=6) for d in range(k)])
+    right = np.column_stack([rng.integers(0, ref.shape[d], size=5) for d in range(k + 1, D)])
+    rows = [list(a) + [i] + list(b) for a in left for i in range(ref.shape[k]) for b in right]
+    C = mirror.eval_grid_indices(np.asarray(rows)).reshape(6 * ref.shape[k], 5)
+    want = np.array([ref[tuple(r)] for r in rows]).reshape(C.shape)
+    scale_close(C.ravel(), want.ravel(), f"{name} cross matrix")
+    with pytest.raises(IndexError):
+        mirror.eval_grid_indices(np.full((1, D), 99))

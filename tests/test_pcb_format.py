@@ -210,3 +210,151 @@ def test_c_host_compiles_against_the_header_and_reports_reference_errors(tmp_pat
     res = subprocess.run([exe, str(bad), str(tmp_path / "pts.f64"), str(tmp_path / "out.f64")],
                          capture_output=True, text=True)
     assert res.returncode == 1 and "bad magic" in res.stderr
+
+
+# ------------------------------------------------------------------------------------------
+# native writer / round trip / grid recipes, no GPU needed
+# ------------------------------------------------------------------------------------------
+
+def _fixture_bytes(gold, name):
+    """Reference-written fixture bytes; approx_5d_bs (62 KB) is rebuilt from its stored tensor and
+    checked against the stored sha256 of the reference's file."""
+    if name == "approx_5d_bs":
+        raw = pcbfile.approx_bytes([[-1.0, 1.0]] * 5, [6] * 5, gold["approx_5d_bs_tensor"])
+    else:
+        raw = gold[name + "_bytes"].tobytes()
+    assert hashlib.sha256(raw).hexdigest() == str(gold[name + "_sha256"])
+    return raw
+
+
+@pytest.mark.parametrize("name", ["approx_2d_simple", "approx_5d_bs", "spline_1d_kink"])
+def test_native_reader_writer_round_trip_is_byte_identical(gold, tmp_path, name):
+    """bytes -> native parser -> native writer -> bytes, on the reference's own fixture files."""
+    from pychebyshev_b200 import _lib
+
+    raw = _fixture_bytes(gold, name)
+    src, dst = tmp_path / "in.pcb", tmp_path / "out.pcb"
+    src.write_bytes(raw)
+    _lib.check(_lib.load().pcb_file_rewrite(str(src).encode(), str(dst).encode()))
+    assert dst.read_bytes() == raw
+
+
+def test_native_writer_matches_reference_written_bytes(gold, tmp_path):
+    from pychebyshev_b200 import _engine
+
+    p = tmp_path / "a.pcb"
+    _engine.write_pcb_native(p, [[0.0, 1.0], [-2.0, 2.0]], [3, 4], gold["approx_3x4_tensor"])
+    assert p.read_bytes() == gold["approx_3x4_bytes"].tobytes()
+    with pytest.raises(ValueError, match="NaN or Inf"):
+        _engine.write_pcb_native(p, [[0.0, 1.0]], [2], np.array([1.0, np.nan]))
+    with pytest.raises(ValueError, match="must be <"):
+        _engine.write_pcb_native(p, [[1.0, 1.0]], [2], np.array([1.0, 2.0]))
+
+
+@pytest.mark.parametrize("name", ["spline_bs2d", "spline_bs3d", "spline_multiknot3d", "spline_abs1d"])
+def test_native_spline_writer_matches_reference_bytes(name, tmp_path):
+    from oracle import np_oracle as O
+    from pychebyshev_b200 import _engine
+
+    g = G.load(name)
+    knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+    n = [int(v) for v in g["piece_n_nodes"][0]]
+    dom = [list(map(float, r)) for r in g["domain"]]
+    p = tmp_path / "s.pcb"
+    _engine.write_pcb_native(p, dom, n, [q[0] for q in pieces], knots=knots)
+    assert p.read_bytes() == g["pcb_bytes"].tobytes()
+
+
+def test_native_grid_recipes_against_numpy():
+    """Nodes / weights / differentiation matrix of the native loader vs the NumPy recipes
+    (barycentric.py:43-77, _extrude_slice.py:66-70).  libm's sin and NumPy's may differ in the last
+    bit, so nodes agree to 1 ulp; given the native nodes, weights and matrix (incl. NumPy's
+    pairwise row sums on the diagonal) are bit-identical."""
+    import ctypes as C
+
+    from pychebyshev_b200 import _grid, _lib
+
+    lib = _lib.load()
+    for lo, hi, n in ((80.0, 120.0, 11), (0.25, 1.0, 16), (-1.0, 1.0, 7), (0.01, 0.08, 33), (0.0, 3.0, 2)):
+        x, w, dm = np.empty(n), np.empty(n), np.empty((n, n))
+        _lib.check(lib.pcb_file_grid_arrays(lo, hi, n, x.ctypes.data_as(_lib._f64p),
+                                            w.ctypes.data_as(_lib._f64p),
+                                            dm.ctypes.data_as(_lib._f64p)))
+        ref_x = _grid.cheb_nodes(lo, hi, n)
+        assert np.all(np.abs(x - ref_x) <= np.spacing(np.abs(ref_x)))
+        assert np.array_equal(w, _grid.bary_weights(x))
+        assert np.array_equal(dm, _grid.diff_matrix(x, w))
+    del C
+
+
+def test_native_loader_bounds_sizes_by_the_file_length(tmp_path):
+    """Crafted headers (huge n_nodes / num_knots / piece counts) are rejected with the reference's
+    EOF error before anything is allocated; no exception crosses the C ABI."""
+    import ctypes as C
+
+    from pychebyshev_b200 import _lib
+
+    lib = _lib.load()
+    head = b"PCB\x00" + bytes([1, 0]) + struct.pack("<H", 1) + b"\x00" * 4
+
+    def approx(n_nodes, payload=b""):
+        D = len(n_nodes)
+        return (head + struct.pack("<I", D) + struct.pack(f"<{D}d", *([0.0] * D)) +
+                struct.pack(f"<{D}d", *([1.0] * D)) + struct.pack(f"<{D}I", *n_nodes) + payload)
+
+    shead = b"PCB\x00" + bytes([1, 0]) + struct.pack("<H", 2) + b"\x00" * 4
+
+    def spline(num_knots, pieces):
+        return (shead + struct.pack("<I", 1) + struct.pack("<d", 0.0) + struct.pack("<d", 1.0) +
+                struct.pack("<I", 4) + struct.pack("<I", num_knots) + struct.pack("<I", pieces))
+
+    cases = [approx([0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF]), approx([0x7FFFFFFF] * 8),
+             approx([1 << 20, 1 << 20], b"\x00" * 64), spline(0xFFFFFFF0, 1), spline(3, 0xFFFFFFFF)]
+    for raw in cases:
+        path = tmp_path / "evil.pcb"
+        path.write_bytes(raw)
+        plan = C.c_void_p()
+        rc = lib.pcb_plan_from_file(0, str(path).encode(), C.byref(plan), None, None)
+        assert rc == _lib.PCB_EINVAL and "unexpected EOF" in _lib.last_error(), _lib.last_error()
+        rc = lib.pcb_file_rewrite(str(path).encode(), str(tmp_path / "o.pcb").encode())
+        assert rc == _lib.PCB_EINVAL
+
+
+@pytest.mark.gpu
+def test_reference_fixture_approx_5d_through_the_native_loader(gold, tmp_path):
+    """tests/fixtures/approx_5d_bs.pcb (6^5): native file -> plan -> values the reference reads out
+    of the same file; with derivative rows: the Python host's plan for the same file."""
+    raw = _fixture_bytes(gold, "approx_5d_bs")
+    path = tmp_path / "approx_5d_bs.pcb"
+    path.write_bytes(raw)
+    plan = pcb.load_plan(path)
+    assert plan.kind == "approx" and plan.ndim == 5 and plan.G == 1
+    got = plan.eval(gold["approx_5d_bs_points"])[:, 0]
+    G.assert_close_scaled(got, gold["approx_5d_bs_values"], 1.0, "approx_5d_bs native loader")
+    orders = [[0] * 5, [1, 0, 0, 0, 0], [0, 0, 2, 0, 0], [0, 1, 0, 1, 0]]
+    plan_g = pcb.load_plan(path, orders=orders)
+    assert plan_g.G == 4
+    host = pcb.ChebyshevApproximation.load(path)
+    want = host.eval_batch_multi(gold["approx_5d_bs_points"], orders)
+    got = plan_g.eval(gold["approx_5d_bs_points"])
+    for j in range(4):
+        G.assert_close_scaled(got[:, j], want[:, j], 1.0, f"file plan order {orders[j]}")
+    with pytest.raises(ValueError, match="entries"):
+        pcb.load_plan(path, orders=[[0, 0]])
+
+
+@pytest.mark.gpu
+def test_spline_file_plan_with_derivative_rows(tmp_path):
+    g = G.load("spline_bs2d")
+    path = tmp_path / "s.pcb"
+    path.write_bytes(g["pcb_bytes"].tobytes())
+    orders = [[0, 0], [1, 0], [0, 1]]
+    plan = pcb.load_plan(path, orders=orders)
+    assert plan.kind == "spline" and plan.G == 3
+    host = pcb.ChebyshevSpline.load(path)
+    pts = g["points"]
+    want = host.eval_batch_multi(pts, orders)
+    got = plan.eval(pts)
+    inside = (pts[:, 0] >= 80.0) & (pts[:, 0] <= 120.0) & (pts[:, 1] >= 0.25) & (pts[:, 1] <= 1.0)
+    for j in range(3):
+        G.assert_close_scaled(got[inside, j], want[inside, j], 1.0, f"spline file plan {orders[j]}")

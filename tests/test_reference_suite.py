@@ -6,9 +6,10 @@ oracle/ref_install.py, git-ignored, shipped to the GPU box).  Each run is a subp
 and rebinds its evaluation methods to the CUDA engine, so every ``vectorized_eval*`` / ``eval*``
 call those tests make is answered by the kernels.
 
-Default: the hot-path files named in SURVEY.md §4 (357 tests).  ``PCB_FULL_REF_SUITE=1`` runs every
-reference test file (algebra, calculus, extrude/slice, ... also evaluate through the patched
-methods).
+Default: the hot-path files named in SURVEY.md §4 with the slowest host-side fixtures thinned
+(see SLOW_K).  ``PCB_FULL_REF_SUITE=hot`` runs those files in full (357 tests);
+``PCB_FULL_REF_SUITE=all`` runs every reference test file (algebra, calculus, extrude/slice, ... also
+evaluate through the patched methods).
 """
 
 import os
@@ -42,8 +43,14 @@ SLOW_K = {
 }
 
 
+def _mode():
+    """'' (default: hot-path files, slow 5-D fixture tests thinned), 'hot' (hot-path files in full),
+    anything else (every reference test file in full)."""
+    return os.environ.get("PCB_FULL_REF_SUITE", "")
+
+
 def _files():
-    if os.environ.get("PCB_FULL_REF_SUITE"):
+    if _mode() not in ("", "hot") and os.path.isdir(REF_TESTS):
         return sorted(f for f in os.listdir(REF_TESTS) if f.startswith("test_") and f.endswith(".py"))
     return HOT_PATH_FILES
 
@@ -58,7 +65,7 @@ def _run(fname, extra=()):
            "ref_suite_plugin", "--rootdir", REF_TESTS, os.path.join(REF_TESTS, fname)]
     for nodeid in DESELECT.get(fname, ()):
         cmd += ["--deselect", os.path.join(REF_TESTS, fname) + "::" + nodeid]
-    if not os.environ.get("PCB_FULL_REF_SUITE") and fname in SLOW_K:
+    if not _mode() and fname in SLOW_K:
         cmd += ["-k", SLOW_K[fname]]
     cmd += list(extra)
     return subprocess.run(cmd, cwd=REF_TESTS, env=env, capture_output=True, text=True,
@@ -72,6 +79,10 @@ def test_reference_test_file_passes_on_b200_backend(fname):
         pytest.skip("reference tests not installed (run python oracle/ref_install.py)")
     res = _run(fname)
     tail = (res.stdout + res.stderr)[-3000:]
+    log = os.environ.get("PCB_REF_SUITE_LOG")
+    if log:
+        with open(log, "a") as f:
+            f.write(f"== {fname}: rc {res.returncode}\n" + "\n".join(res.stdout.splitlines()[-6:]) + "\n")
     assert res.returncode == 0, tail
     m = re.search(r"B200_BACKEND installed=True kernel_launches=(\d+)", res.stdout)
     assert m, tail
