@@ -200,7 +200,8 @@ class FullCase(Case):
         self.flop_q = self.G * full_flops(self.n_nodes)
         self.flop_note = "G x 2 sum_k prod_{j<=k} n_j (weight rows not counted)"
         self.bytes_q = 8.0 * (self.D + self.G)
-        self.kernel = "full_dmma_kernel"
+        self.kernel = ("full_dmma2_kernel (joint-K)" if which == "bs5d" and not os.environ.get("PCB_NO_DMMA2")
+                       else "full_dmma_kernel")
 
     def obj(self, dev):
         import pychebyshev_b200 as pcb
@@ -255,7 +256,8 @@ class SplineCase(Case):
             self.flop_note = ("G x 2 sum_k prod_{j<=k} n_j + product-form weight rows "
                               "(6 ops per node + 1/sum per dim)")
             self.bytes_q = 8.0 * (dim + self.G)
-            self.kernel = "spline_bank_kernel"
+            self.kernel = ("spline2d_dmma_kernel" if dim == 2 and not os.environ.get("PCB_NO_DMMA2D")
+                           else "spline_bank_kernel")
 
     def obj(self, dev):
         import pychebyshev_b200 as pcb
@@ -313,7 +315,7 @@ class SliderCase(Case):
         self.flop_q = 5 * (full_flops([11, 11]) + weight_row_flops([11, 11]))
         self.flop_note = "5 slides x (2 (121+11) + product-form weight rows)"
         self.bytes_q = 8.0 * (self.D + self.G)
-        self.kernel = "slider_bank_kernel"
+        self.kernel = "slider_bank_kernel" if os.environ.get("PCB_NO_DMMA2D") else "slider2d_dmma_kernel"
 
     def obj(self, dev):
         import _golden as G

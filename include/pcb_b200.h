@@ -122,7 +122,8 @@ PCB_API int pcb_full_plan_create_from_values(int dev, int D, const int32_t *n, c
 
 /* Replaces G calls of ChebyshevApproximation.vectorized_eval_batch (barycentric.py:992-1047),
  * one per pre-differentiated tensor: d_out (N, G).  `algo`: 0 = auto, 1 = thread-per-query FMA
- * evaluator, 2 = DMMA mode-1 GEMM with fused tail (D >= 3). */
+ * evaluator, 2 = DMMA mode-1 GEMM with fused tail (D >= 2), 3 = DMMA GEMM over the last TWO axes
+ * jointly (D >= 3; chosen by auto when the last axis is not a multiple of 4). */
 PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t N, double *d_out, int algo,
                   void *stream);
 

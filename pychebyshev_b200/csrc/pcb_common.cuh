@@ -59,10 +59,11 @@ int tensor_mode_launch(int dev, const double *d_src, double *d_dst, long long ou
 // value would race with a concurrent launch of the same kernel that needs more.
 template <typename K>
 inline cudaError_t allow_dynamic_smem(K kernel, size_t smem, int smem_optin) {
-    if (smem <= 48 * 1024) return cudaSuccess;  // within the default limit
+    if (smem <= 40 * 1024) return cudaSuccess;  // safely within the default 48 KB incl. static
     cudaFuncAttributes attr;
     const cudaError_t e = cudaFuncGetAttributes(&attr, reinterpret_cast<const void *>(kernel));
     if (e != cudaSuccess) return e;
+    if (smem + attr.sharedSizeBytes <= 48 * 1024) return cudaSuccess;  // static + dynamic fit
     // the opt-in maximum covers static + dynamic shared memory
     return cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel),
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,

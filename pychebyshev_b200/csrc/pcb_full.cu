@@ -46,6 +46,34 @@ struct DmmaParams {
     int node_off[PCB_MAX_DIMS];
 };
 
+// Joint-K variant (round 2): the LAST TWO axes (d, e) are flattened into the MMA K dimension,
+// K = n_d * n_e padded to a multiple of 4, with the A operand A[q, (d, e)] = w_d(q) * w_e(q) built
+// once per query tile and held in REGISTERS (KB x 2 row tiles per lane; a first version that re-read
+// A from shared memory for every slab measured 55 % on 11^5 -- one LDS per DMMA with four consumer
+// warps -- against 66 % for the per-row variant).  Against the variant above this (i) pads K once
+// (11 x 11 = 121 -> 124, 97.6 %, instead of 11 -> 12, 91.7 %, per row) and (ii) needs no per-d
+// weighted fold on the FP64 pipe (8 DFMA per 12 DMMA), which together cap the 11^5 case at 79.5 % of
+// the pipe; joint-K caps at 0.976 x 0.945 (121 leading positions in 128 columns) = 92 %.
+constexpr int DM2_WARPS = 8;                        // consumer warps per CTA
+constexpr int DM2_MT = 2;                           // 8-query row tiles per warp (A fragments in registers)
+constexpr int DM2_QT = DM2_WARPS * DM2_MT * 8;      // 128 queries per CTA tile
+constexpr int DM2_THREADS = (DM2_WARPS + 1) * 32;   // + 1 producer warp
+constexpr int DM2_MAX_KB = 36;                      // K <= 144 (12 x 12); larger K keeps the per-row variant
+
+struct Dmma2Params {
+    int D, G;
+    int n[PCB_MAX_DIMS];
+    int woff[PCB_MAX_DIMS];   // rows of the weight table for dims < D - 2
+    int node_off[PCB_MAX_DIMS];
+    int n_lead_dims, L, LG;   // dims [0, n_lead_dims) flattened into the MMA column axis
+    int nc, dim_c;            // the folded middle axis (-1 / 1 when absent)
+    int K, KB;                // n[D-2] * n[D-1], ceil(K / 4)
+    int wrows;                // rows of the weight table
+    int slab;                 // doubles per (lead group, c) slab = KB * 32
+    int stages;
+    long long gstride;        // doubles per prepared tensor
+};
+
 struct FullPlan : PlanBase {
     void *small = nullptr;  // one-piece spline plan on the constant bank (small tensors), or null
     GridDesc gd;
@@ -58,7 +86,12 @@ struct FullPlan : PlanBase {
     bool dmma_ok = false;
     DmmaParams dm;
     size_t dm_smem = 0;
+    double *d_prepared2 = nullptr;  // joint-K fragment order
+    bool dmma2_ok = false;
+    Dmma2Params dm2;
+    size_t dm2_smem = 0;
     ~FullPlan() override {
+        if (d_prepared2) cudaFree(d_prepared2);
         if (small) pcb_plan_destroy(small);
         if (d_nodes) cudaFree(d_nodes);
         if (d_tensors) cudaFree(d_tensors);
@@ -358,6 +391,201 @@ full_dmma_kernel(const __grid_constant__ DmmaParams P, const double *__restrict_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// joint-K DMMA kernel
+// ---------------------------------------------------------------------------------------------
+struct Dmma2Smem {
+    int w, ring, bars, total;  // doubles
+};
+__host__ __device__ inline Dmma2Smem dmma2_smem_layout(const Dmma2Params &P) {
+    Dmma2Smem L;
+    L.w = 0;
+    L.ring = L.w + P.wrows * DM2_QT;
+    int ring = P.stages * P.slab;
+    const int scratch = (P.n[P.D - 2] + P.n[P.D - 1]) * DM2_QT;  // the two last weight rows (prologue)
+    if (ring < scratch) ring = scratch;
+    L.bars = L.ring + ring;
+    L.total = L.bars + 2 * DM_MAX_STAGES;
+    return L;
+}
+
+template <int KB>
+__global__ void __launch_bounds__(DM2_THREADS, 1)
+full_dmma2_kernel(const __grid_constant__ Dmma2Params P, const double *__restrict__ nodes,
+                  const double *__restrict__ weights, const double *__restrict__ prepared,
+                  const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
+    extern __shared__ __align__(128) double smem[];
+    const Dmma2Smem L = dmma2_smem_layout(P);
+    double *w_s = smem + L.w;
+    double *ring = smem + L.ring;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint64_t *empty = full + DM_MAX_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = P.D, nd = P.n[D - 2], ne = P.n[D - 1];
+    const int64_t ntiles = (N + DM2_QT - 1) / DM2_QT;
+    const uint32_t slab_bytes = (uint32_t)P.slab * 8u;
+    const int slabs_per_g = P.LG * P.nc;
+    if (tid == 0) {
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], DM2_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t it = 0;  // slabs handled so far by this thread's role (ring position persists across tiles)
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t q0 = tile * DM2_QT;
+        __syncthreads();  // previous tile done: ring drained, tables free
+        // ---- prologue 1: barycentric weight rows (K-A0); the two last dims go to the ring scratch
+        for (int e = tid; e < DM2_QT * D; e += DM2_THREADS) {
+            const int ql = e % DM2_QT, d = e / DM2_QT;
+            int64_t q = q0 + ql;
+            if (q >= N) q = N - 1;
+            const double x = __ldg(pts + q * D + d);
+            double *dst = d == D - 1 ? ring + (size_t)nd * DM2_QT + ql
+                                     : (d == D - 2 ? ring + ql : w_s + (size_t)P.woff[d] * DM2_QT + ql);
+            grid_weight_row(x, P.n[d], nodes + P.node_off[d], weights + P.node_off[d], dst, DM2_QT);
+        }
+        __syncthreads();
+        // ---- prologue 2 (consumers): A fragments A[q, k] = w_d(q)[k / ne] * w_e(q)[k % ne] into
+        //      registers, k = 4 kb + (lane & 3), q = this lane's rows; zero beyond K
+        const int qrow = (warp < DM2_WARPS ? warp : 0) * (DM2_MT * 8) + (lane >> 2);
+        const int kcol = lane & 3;
+        double afrag[KB][DM2_MT];
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            const int k = 4 * kb + kcol;
+            const bool live_k = k < P.K;
+            const int kd = live_k ? k / ne : 0, ke = live_k ? k - kd * ne : 0;
+#pragma unroll
+            for (int mt = 0; mt < DM2_MT; ++mt) {
+                const int ql = qrow + mt * 8;
+                const double v = ring[(size_t)kd * DM2_QT + ql] * ring[(size_t)(nd + ke) * DM2_QT + ql];
+                afrag[kb][mt] = live_k ? v : 0.0;
+            }
+        }
+        __syncthreads();  // scratch consumed: the producer may overwrite the ring
+        if (warp == DM2_WARPS) {
+            if (lane == 0) {
+                for (int g = 0; g < P.G; ++g) {
+                    const double *src = prepared + (size_t)g * P.gstride;
+                    for (int sidx = 0; sidx < slabs_per_g; ++sidx, ++it) {
+                        const int s = it % P.stages;
+                        const uint32_t round = it / P.stages;
+                        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+                        mbar_arrive_expect_tx(&full[s], slab_bytes);
+                        bulk_g2s(ring + (size_t)s * P.slab, src + (size_t)sidx * P.slab, slab_bytes, &full[s]);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            for (int g = 0; g < P.G; ++g) {
+                double outacc[DM2_MT];
+#pragma unroll
+                for (int mt = 0; mt < DM2_MT; ++mt) outacc[mt] = 0.0;
+                for (int lg = 0; lg < P.LG; ++lg) {
+                    double acc3[DM2_MT][2];
+#pragma unroll
+                    for (int mt = 0; mt < DM2_MT; ++mt) acc3[mt][0] = acc3[mt][1] = 0.0;
+                    for (int c = 0; c < P.nc; ++c, ++it) {
+                        const int s = it % P.stages;
+                        mbar_wait(&full[s], (it / P.stages) & 1);
+                        const double *slab = ring + (size_t)s * P.slab + lane;
+                        // two accumulator sets (even / odd k-blocks): four independent MMA chains
+                        // per warp, so a chain's latency does not gate the tensor pipe
+                        double acc2[DM2_MT][2], accb[DM2_MT][2];
+#pragma unroll
+                        for (int mt = 0; mt < DM2_MT; ++mt)
+                            acc2[mt][0] = acc2[mt][1] = accb[mt][0] = accb[mt][1] = 0.0;
+#pragma unroll
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const double b = slab[kb * 32];
+#pragma unroll
+                            for (int mt = 0; mt < DM2_MT; ++mt) {
+                                if (kb & 1)
+                                    dmma884(accb[mt][0], accb[mt][1], afrag[kb][mt], b);
+                                else
+                                    dmma884(acc2[mt][0], acc2[mt][1], afrag[kb][mt], b);
+                            }
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < DM2_MT; ++mt) {
+                            acc2[mt][0] += accb[mt][0];
+                            acc2[mt][1] += accb[mt][1];
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[s]);
+                        if (P.dim_c >= 0) {
+                            const double *wc = w_s + (size_t)(P.woff[P.dim_c] + c) * DM2_QT + qrow;
+#pragma unroll
+                            for (int mt = 0; mt < DM2_MT; ++mt) {
+                                const double w = wc[mt * 8];
+                                acc3[mt][0] = fma(w, acc2[mt][0], acc3[mt][0]);
+                                acc3[mt][1] = fma(w, acc2[mt][1], acc3[mt][1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int mt = 0; mt < DM2_MT; ++mt) {
+                                acc3[mt][0] = acc2[mt][0];
+                                acc3[mt][1] = acc2[mt][1];
+                            }
+                        }
+                    }
+                    // fold the leading axes: this lane owns columns 2 kcol, 2 kcol + 1 of the group
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int p = lg * 8 + kcol * 2 + e;
+                        if (p < P.L) {
+#pragma unroll
+                            for (int mt = 0; mt < DM2_MT; ++mt) {
+                                double wl = 1.0;
+                                int rem = p;
+                                for (int dd = P.n_lead_dims - 1; dd >= 0; --dd) {
+                                    const int idx = rem % P.n[dd];
+                                    rem /= P.n[dd];
+                                    wl *= w_s[(size_t)(P.woff[dd] + idx) * DM2_QT + qrow + mt * 8];
+                                }
+                                outacc[mt] = fma(wl, acc3[mt][e], outacc[mt]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < DM2_MT; ++mt) {
+                    double v = outacc[mt];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int64_t q = q0 + qrow + mt * 8;
+                    if (kcol == 0 && q < N) out[q * P.G + g] = v;
+                }
+            }
+        }
+    }
+}
+
+// prepared2[((lg * nc + c) * KB + kb) * 32 + lane] = T[lead = 8 lg + lane/4][c][k = 4 kb + lane%4]
+__global__ void __launch_bounds__(256)
+dmma2_prepare_kernel(const __grid_constant__ Dmma2Params P, const double *__restrict__ t,
+                     double *__restrict__ dst) {
+    const long long s_c = P.K;
+    const long long s_lead = s_c * P.nc;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < P.gstride;
+         o += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(o & 31);
+        long long r = o >> 5;
+        const int kb = (int)(r % P.KB);
+        r /= P.KB;
+        const int c = (int)(r % P.nc);
+        const long long lg = r / P.nc;
+        const long long lead = lg * 8 + lane / 4;
+        const int k = kb * 4 + lane % 4;
+        dst[o] = (lead < P.L && k < P.K) ? t[lead * s_lead + c * s_c + k] : 0.0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -456,6 +684,82 @@ static bool dmma_configure(FullPlan *pl, const int32_t *n) {
         }
     }
     return false;
+}
+
+
+// Joint-K variant: worth it when the last axis is not a multiple of 4 (or the per-d fold hurts) and
+// the A table fits in shared memory.
+static bool dmma2_configure(FullPlan *pl, const int32_t *n) {
+    const int D = pl->gd.D;
+    if (D < 3 || getenv("PCB_NO_DMMA2")) return false;
+    Dmma2Params &P = pl->dm2;
+    memset(&P, 0, sizeof(P));
+    P.D = D;
+    P.G = pl->G;
+    int off = 0, woff = 0;
+    for (int d = 0; d < D; ++d) {
+        P.n[d] = n[d];
+        P.node_off[d] = off;
+        off += n[d];
+        P.woff[d] = woff;
+        if (d < D - 2) woff += n[d];
+    }
+    P.wrows = woff;
+    P.K = n[D - 2] * n[D - 1];
+    P.KB = (P.K + 3) / 4;
+    if (P.KB > DM2_MAX_KB) return false;
+    // the kernel is instantiated for a few K-block counts (A fragments live in registers, so the kb
+    // loop must unroll); round up to the next one (the extra rows are zero in A and in the slabs)
+    static const int kb_classes[] = {16, 21, 25, 31, 36};
+    for (int kc : kb_classes)
+        if (P.KB <= kc) {
+            P.KB = kc;
+            break;
+        }
+    // one folded middle axis when the flattened leading axes still fill the 8-wide column tiles
+    P.dim_c = -1;
+    P.nc = 1;
+    P.n_lead_dims = D - 2;
+    if (D >= 4) {
+        long long Lc = 1;
+        for (int d = 0; d < D - 3; ++d) Lc *= n[d];
+        const double eff = (double)Lc / (double)(((Lc + 7) / 8) * 8);
+        if (eff >= 0.9) {
+            P.dim_c = D - 3;
+            P.nc = n[D - 3];
+            P.n_lead_dims = D - 3;
+        }
+    }
+    long long L = 1;
+    for (int d = 0; d < P.n_lead_dims; ++d) L *= n[d];
+    if (L > (1 << 28)) return false;
+    P.L = (int)L;
+    P.LG = (P.L + 7) / 8;
+    P.slab = P.KB * 32;
+    P.gstride = (long long)P.LG * P.nc * P.slab;
+    for (int st = DM_MAX_STAGES; st >= 2; --st) {
+        P.stages = st;
+        const Dmma2Smem Ls = dmma2_smem_layout(P);
+        if ((size_t)Ls.total * 8 <= (size_t)pl->smem_optin) {
+            pl->dm2_smem = (size_t)Ls.total * 8;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Predicted FP64-pipe efficiency of the two tensor-core variants (useful work / pipe time).
+static double dmma_eff(const FullPlan *pl) {
+    const DmmaParams &P = pl->dm;
+    const int ne = P.n[P.D - 1];
+    const double kpad = (double)ne / (4.0 * P.KB);
+    const double lpad = (double)P.L / (8.0 * P.LG);
+    const double fold = P.dim_d >= 0 ? (double)(P.KB * 8) / (double)(P.KB * 8 + 1) : 1.0;  // 1 DFMA-pair per KB DMMAs
+    return kpad * lpad * fold;
+}
+static double dmma2_eff(const FullPlan *pl) {
+    const Dmma2Params &P = pl->dm2;
+    return ((double)P.K / (4.0 * P.KB)) * ((double)P.L / (8.0 * P.LG));
 }
 
 }  // namespace pcb
@@ -604,6 +908,14 @@ static int full_plan_build(int dev, int D, const int32_t *n, const double *nodes
         cudaGetLastError();
         pl->dmma_ok = false;
     }
+    pl->dmma2_ok = dmma2_configure(pl, n);
+    if (pl->dmma2_ok && pl->dmma_ok && dmma2_eff(pl) <= dmma_eff(pl) + 0.02 && !getenv("PCB_FORCE_DMMA2"))
+        pl->dmma2_ok = false;  // the per-row variant is as good (last axis a multiple of 4)
+    if (pl->dmma2_ok &&
+        cudaMalloc(&pl->d_prepared2, (size_t)pl->dm2.gstride * sizeof(double) * G) != cudaSuccess) {
+        cudaGetLastError();
+        pl->dmma2_ok = false;
+    }
     const bool want_small = D <= 4 && gd.size * G <= 8192;
     std::vector<std::vector<double>> small_t;
     const int grid = (int)std::min<long long>((gd.size + 255) / 256, (long long)pl->sm_count * 32);
@@ -618,6 +930,10 @@ static int full_plan_build(int dev, int D, const int32_t *n, const double *nodes
         if (pl->dmma_ok) {
             const int pg = (int)std::min<long long>((pl->dm.gstride + 255) / 256, (long long)pl->sm_count * 32);
             dmma_prepare_kernel<<<pg, 256>>>(pl->dm, t, pl->d_prepared + (size_t)g * pl->dm.gstride);
+        }
+        if (pl->dmma2_ok) {
+            const int pg = (int)std::min<long long>((pl->dm2.gstride + 255) / 256, (long long)pl->sm_count * 32);
+            dmma2_prepare_kernel<<<pg, 256>>>(pl->dm2, t, pl->d_prepared2 + (size_t)g * pl->dm2.gstride);
         }
         if (want_small) {
             const double *h = src.host(g);
@@ -702,18 +1018,42 @@ static int launch_dmma(FullPlan *pl, const double *d_points, int64_t N, double *
     return PCB_OK;
 }
 
+template <int KB>
+static int launch_dmma2(FullPlan *pl, const double *d_points, int64_t N, double *d_out, cudaStream_t st) {
+    PCB_CUDA(allow_dynamic_smem(full_dmma2_kernel<KB>, pl->dm2_smem, pl->smem_optin));
+    const int64_t ntiles = (N + DM2_QT - 1) / DM2_QT;
+    const int grid = (int)(ntiles < pl->sm_count ? ntiles : pl->sm_count);
+    full_dmma2_kernel<KB><<<grid, DM2_THREADS, pl->dm2_smem, st>>>(pl->dm2, pl->d_nodes, pl->d_weights,
+                                                                 pl->d_prepared2, d_points, N, d_out);
+    g_launches.fetch_add(1);
+    PCB_CUDA(cudaGetLastError());
+    return PCB_OK;
+}
+
 extern "C" PCB_API int pcb_full_eval(void *plan, const double *d_points, int64_t N, double *d_out, int algo,
                              void *stream) {
     FullPlan *pl = static_cast<FullPlan *>(plan);
     PCB_REQUIRE(pl && pl->kind == PLAN_FULL, "not a full-tensor plan");
     PCB_REQUIRE(N >= 0, "negative N");
-    PCB_REQUIRE(algo >= 0 && algo <= 2, "algo %d not available", algo);
+    PCB_REQUIRE(algo >= 0 && algo <= 3, "algo %d not available", algo);
     if (N == 0) return PCB_OK;
     PCB_REQUIRE(d_points && d_out, "null device pointer");
     DeviceGuard guard(pl->dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (algo == 2 && !pl->dmma_ok)
         return fail(PCB_EUNSUPPORTED, "tensor-core path not available for this shape");
+    if (algo == 3 && !pl->dmma2_ok)
+        return fail(PCB_EUNSUPPORTED, "joint-K tensor-core path not available for this shape");
+    if (algo == 3 || (algo == 0 && pl->dmma2_ok && pl->gd.size >= 4096 && N >= 64)) {
+        switch (pl->dm2.KB) {
+            case 16: return launch_dmma2<16>(pl, d_points, N, d_out, st);
+            case 21: return launch_dmma2<21>(pl, d_points, N, d_out, st);
+            case 25: return launch_dmma2<25>(pl, d_points, N, d_out, st);
+            case 31: return launch_dmma2<31>(pl, d_points, N, d_out, st);
+            case 36: return launch_dmma2<36>(pl, d_points, N, d_out, st);
+        }
+        return fail(PCB_EUNSUPPORTED, "joint-K tensor-core path: no instantiation for %d K-blocks", pl->dm2.KB);
+    }
     // auto: the tensor-core GEMM once the tensor is big enough to amortise a 256-query tile
     const bool use_dmma = algo == 2 || (algo == 0 && pl->dmma_ok && pl->gd.size >= 4096 && N >= 64);
     if (use_dmma) {

@@ -272,7 +272,7 @@ __device__ __forceinline__ double bank_rcp(double s) {
 // N is a template argument (dispatched by a uniform switch) so that no per-node guard is needed:
 // ptxas if-converts such guards into per-lane predicates, which drags the bank reads off the
 // uniform path.
-template <int N, bool STORE>
+template <int N, int STORE>
 __device__ __forceinline__ double bank_row_n(double x, int nbase, int wbase, long long eps_bits,
                                              double (&a)[GRID_NL], double *ws, int wstride, double fold) {
     double d[N];
@@ -299,7 +299,11 @@ __device__ __forceinline__ double bank_row_n(double x, int nbase, int wbase, lon
         for (int i = 0; i < N; ++i) a[i] = i == hit ? 1.0 : 0.0;
         sum = 1.0;
     }
-    if constexpr (STORE) {
+    if constexpr (STORE == 2) {
+        // raw (unnormalised) row to the smem column, zero-padded to GRID_NL entries
+#pragma unroll
+        for (int i = 0; i < GRID_NL; ++i) ws[i * wstride] = i < N ? a[i] : 0.0;
+    } else if constexpr (STORE == 1) {
         // normalised row to the smem column; `fold` carries the last row's 1/sum into dim 0
         const double inv = bank_rcp(sum);
 #pragma unroll
@@ -314,9 +318,10 @@ __device__ __forceinline__ double bank_row_n(double x, int nbase, int wbase, lon
 #define BANK_ROW_CASE(K) \
     case K: return bank_row_n<K, STORE>(x, nbase, wbase, eps_bits, a, ws, wstride, fold);
 
-// Row of an n-node dimension: STORE ? normalised (times `fold`) into the smem column ws :
-// unnormalised in a[] (entries >= n zero).  Returns the row sum.
-template <bool STORE>
+// Row of an n-node dimension.  STORE 1: normalised (times `fold`) into the smem column ws; 0:
+// unnormalised in a[] (entries >= n zero); 2: unnormalised into the smem column, zero-padded to
+// GRID_NL entries.  Returns the row sum.
+template <int STORE>
 __device__ __forceinline__ double bank_row(double x, int n, int nbase, int wbase, long long eps_bits,
                                            double (&a)[GRID_NL], double *ws, int wstride, double fold) {
     static_assert(GRID_NL == 16, "the bank path dispatches 1..16 nodes");
@@ -585,7 +590,7 @@ constexpr int BL_SA = 36, BL_SB = 34;           // padded strides (doubles) of t
 constexpr int BL_FRAG = 256;                    // doubles per (grid, output): 4 k-blocks x 2 n-tiles x 32 lanes
 constexpr int BL_MAX_FRAGS = 24;                // staged in shared memory (48 KB)
 constexpr int BL_OUT = 4;                       // outputs folded per pass
-constexpr int BL_WARP_DOUBLES = 16 * BL_SA + 16 * BL_SB + BL_OUT * 32;
+constexpr int BL_WARP_DOUBLES = 16 * BL_SA + 16 * BL_SB + BL_OUT * 32 + 32;  // tiles, outputs, scratch row
 
 __device__ __forceinline__ void bl_dmma(double &c0, double &c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -593,62 +598,73 @@ __device__ __forceinline__ void bl_dmma(double &c0, double &c1, double a, double
         : "d"(a), "d"(b));
 }
 
-// Weight rows of bank grid `g` for this lane's query into the warp tile (predicated on `keep`);
-// returns 1 / (sum a * sum b) (1-D factors folded) for the lanes that keep it.
+// Weight rows of bank grid `g` for this lane's query into the warp tile (lanes that do not `keep`
+// write a scratch row instead); returns 1 / (sum a * sum b).
+// The rows are stored from INSIDE bank_row_n's per-length cases (mode 2): merging a register row out
+// of the switch and storing it afterwards takes every bank read of the kernel off the uniform
+// datapath -- and so does a register cap (`__launch_bounds__(.., minBlocks)`), which is why these
+// kernels carry none (they need 72-78 registers).
 template <typename Coord>
 __device__ __forceinline__ double bl_rows(const BankGrid &g, Coord x, bool keep, double *sA, double *sB,
                                           int lane) {
     double row[GRID_NL];
-    const double sa = bank_row<false>(x(0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
-                                      __double_as_longlong(c_grid[g.scale_off + 2 + 0]), row, nullptr, 0, 1.0);
-    if (keep) {
-#pragma unroll
-        for (int i = 0; i < GRID_NL; ++i) sA[i * BL_SA + lane] = row[i];
-    }
-    const double sb = bank_row<false>(x(1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
-                                      g.weight_off + g.n[0],
-                                      __double_as_longlong(c_grid[g.scale_off + 2 + 1]), row, nullptr, 0, 1.0);
-    if (keep) {
-#pragma unroll
-        for (int j = 0; j < GRID_NL; ++j) sB[j * BL_SB + lane] = row[j];
-    }
+    double *dump = sA + 16 * BL_SA + 16 * BL_SB + BL_OUT * 32;  // 32 doubles per warp
+    const double sa = bank_row<2>(x(0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
+                                  __double_as_longlong(c_grid[g.scale_off + 2 + 0]), row,
+                                  (keep ? sA : dump) + lane, keep ? BL_SA : 0, 1.0);
+    const double sb = bank_row<2>(x(1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
+                                  g.weight_off + g.n[0],
+                                  __double_as_longlong(c_grid[g.scale_off + 2 + 1]), row,
+                                  (keep ? sB : dump) + lane, keep ? BL_SB : 0, 1.0);
     return bank_rcp(sa * sb);
 }
 
-// Row tile t (queries 8t..8t+7 of the warp) against grid `g`, outputs [o0, o0 + no): the lanes
-// with (lane & 3) == 0 whose row passes `take` write sOut[o * 32 + row].
-__device__ __forceinline__ void bl_tile(const BankGrid &g, const double *frag, int o0, int no, int t,
-                                        const double *sA, const double *sB, double *sOut, int lane,
-                                        bool take) {
+// Row tile t (queries 8t..8t+7 of the warp) against one grid, outputs [o0, o0 + no): the lanes with
+// (lane & 3) == 0 whose row passes `take` write sOut[o * 32 + row].  KB = ceil(n0 / 4) k-blocks and
+// NT = ceil(n1 / 8) column tiles are template arguments (dispatched by a uniform switch): runtime
+// guards cost an ISETP + SEL per fragment element, more than the MMAs themselves.
+template <int KB, int NT>
+__device__ __forceinline__ void bl_tile_n(const double *frag, int o0, int no, int t, const double *sA,
+                                          const double *sB, double *sOut, int lane, bool take) {
     const int r = lane >> 2, c = lane & 3;
-    const int KB = (g.n[0] + 3) >> 2, NT = (g.n[1] + 7) >> 3;
-    double af[4];
+    double af[KB];
 #pragma unroll
-    for (int kb = 0; kb < 4; ++kb) af[kb] = kb < KB ? sA[(4 * kb + c) * BL_SA + 8 * t + r] : 0.0;
-    double bq[2][2];
+    for (int kb = 0; kb < KB; ++kb) af[kb] = sA[(4 * kb + c) * BL_SA + 8 * t + r];
+    double bq[NT][2];
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-            bq[nt][e] = nt < NT ? sB[(8 * nt + 2 * c + e) * BL_SB + 8 * t + r] : 0.0;
+        for (int e = 0; e < 2; ++e) bq[nt][e] = sB[(8 * nt + 2 * c + e) * BL_SB + 8 * t + r];
     for (int o = 0; o < no; ++o) {
         const double *f = frag + (size_t)(o0 + o) * BL_FRAG + lane;
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double acc[NT][2];
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-            if (kb < KB) {
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-                    if (nt < NT) bl_dmma(acc[nt][0], acc[nt][1], af[kb], f[(kb * 2 + nt) * 32]);
-            }
-        }
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bl_dmma(acc[nt][0], acc[nt][1], af[kb], f[(kb * 2 + nt) * 32]);
         double part = acc[0][0] * bq[0][0];
         part = fma(acc[0][1], bq[0][1], part);
-        part = fma(acc[1][0], bq[1][0], part);
-        part = fma(acc[1][1], bq[1][1], part);
+        if constexpr (NT > 1) {
+            part = fma(acc[1][0], bq[1][0], part);
+            part = fma(acc[1][1], bq[1][1], part);
+        }
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         if (c == 0 && take) sOut[o * 32 + 8 * t + r] = part;
+    }
+}
+
+#define BL_TILE_CASE(KBV, NTV) \
+    case (KBV) * 2 + (NTV): bl_tile_n<KBV, NTV>(frag, o0, no, t, sA, sB, sOut, lane, take); break;
+
+__device__ __forceinline__ void bl_tile(const BankGrid &g, const double *frag, int o0, int no, int t,
+                                        const double *sA, const double *sB, double *sOut, int lane,
+                                        bool take) {
+    switch (((g.n[0] + 3) >> 2) * 2 + ((g.n[1] + 7) >> 3)) {
+        BL_TILE_CASE(1, 1) BL_TILE_CASE(1, 2) BL_TILE_CASE(2, 1) BL_TILE_CASE(2, 2)
+        BL_TILE_CASE(3, 1) BL_TILE_CASE(3, 2) BL_TILE_CASE(4, 1) BL_TILE_CASE(4, 2)
     }
 }
 
@@ -656,7 +672,7 @@ __device__ __forceinline__ void bl_stage_frags(double *sFrag, const double *__re
     for (int e = threadIdx.x; e < nfrag * BL_FRAG; e += BL_THREADS) sFrag[e] = __ldg(frags + e);
 }
 
-__global__ void __launch_bounds__(BL_THREADS, 4)
+__global__ void __launch_bounds__(BL_THREADS)
 spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
                      const double *__restrict__ knots, const double *__restrict__ frags,
                      const double *__restrict__ pts, int64_t N, double *__restrict__ out,
@@ -730,7 +746,7 @@ spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int 
 
 // Slider of 2-D slides: value rows accumulate pivot + sum_s (slide_s - pivot) left to right
 // (slider.py:310-318), a derivative row takes its slide's output, cross-slide rows are exactly 0.
-__global__ void __launch_bounds__(BL_THREADS, 4)
+__global__ void __launch_bounds__(BL_THREADS)
 slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ out_slide,
                      const int *__restrict__ row_out, const int *__restrict__ frag_off, int nfrag,
                      const double *__restrict__ frags, const double *__restrict__ pts, int64_t N,

@@ -160,7 +160,7 @@ __device__ __forceinline__ void ttc_coeff_pass(int base, int w, int r_rows, int 
 }
 
 // ---- values ------------------------------------------------------------------------------------------
-template <int QPT, int RMAX, int MAXT, int MINB = 1>
+template <int QPT, int RMAX, int MAXT, int MINB = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
 ttc_value_kernel(const __grid_constant__ TTParams P, const double *__restrict__ pts, int64_t N,
                  double *__restrict__ out) {
@@ -187,7 +187,7 @@ ttc_value_kernel(const __grid_constant__ TTParams P, const double *__restrict__ 
 }
 
 // ---- pcb_tt_eval_fd algo 2 (see pcb_tt_shared.cu for the algorithm) -----------------------------------
-template <int QPT, int RMAX, int MAXT, int MINB = 1>
+template <int QPT, int RMAX, int MAXT, int MINB = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
 ttc_fd_shared_kernel(const __grid_constant__ TTParams P, const __grid_constant__ TTSharedProgram prog,
                      const double *__restrict__ pts, int64_t N, double *__restrict__ out) {
@@ -406,8 +406,11 @@ __device__ __forceinline__ void ttc_ychunk(int base, int r_rows, int n, const do
     }
 }
 
+// (minBlocks = 3 is a register budget, not an occupancy target -- shared memory admits one CTA per
+// SM at rank 20: at 80 registers ptxas keeps 87 % of the bank reads on the uniform datapath, at the
+// unbounded 127 only 25 %; tools/check_sass.py)
 template <int QPT, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, 3)
 ttc_gcoeff_kernel(const __grid_constant__ TTGCoeff a, const double *__restrict__ pts, int64_t N) {
     constexpr int RMAX = 16;
     extern __shared__ __align__(16) double smem[];
@@ -599,14 +602,16 @@ struct TTCSharedVariant {
 // first entry of a rank class = its default; B = 2: two CTAs per SM, so one CTA's coordinate loads,
 // chain-vector initialisation and stores overlap the other's arithmetic
 static const TTCValueVariant kValueVariants[] = {
-    // values: two 512-thread CTAs per SM (64 registers per thread, 32 resident warps) measure
-    // 3.6e9 values/s on the 5-D train against 2.05e9 for one CTA at 122 registers
-    VV(2, 8, 512, 2), VV(2, 12, 512, 2), VV(2, 16, 512, 2),
-    VV(2, 12, 512, 1), VV(3, 12, 320, 1), VV(2, 12, 256, 2), VV(2, 16, 512, 1),
+    // B = 0: no minBlocks bound (the register budget follows from the thread count alone); B = 2: two
+    // CTAs per SM.  ptxas' uniform-datapath decision depends on the register budget it is given
+    // (tools/check_sass.py): <2,12,512> keeps its bank reads on LDCU at 64 registers (B = 2) and
+    // loses them at 122 (B = 0/1) -- 3.6e9 against 2.05e9 values/s on the 5-D train.
+    VV(2, 8, 512, 2), VV(2, 12, 512, 2), VV(2, 16, 512, 0),
+    VV(3, 12, 320, 0), VV(2, 16, 512, 2),
 };
 static const TTCSharedVariant kSharedVariants[] = {
-    SV(2, 8, 512, 1), SV(2, 12, 512, 1), SV(2, 16, 384, 1),
-    SV(2, 12, 384, 1), SV(2, 12, 256, 2), SV(2, 8, 256, 2), SV(1, 12, 512, 2),
+    SV(2, 8, 512, 0), SV(2, 12, 512, 0), SV(2, 16, 384, 0),
+    SV(2, 12, 384, 0), SV(2, 12, 256, 2), SV(2, 8, 256, 2),
 };
 #undef VV
 #undef SV
@@ -614,7 +619,8 @@ static const TTCSharedVariant kSharedVariants[] = {
 template <typename V, size_t NV>
 static const V *ttc_pick(const V (&tab)[NV], const TTPlan *pl, int qpt, int threads, int rc_, int nbuf) {
     auto fits = [&](const V &v) {  // all resident CTAs of an SM share its shared memory
-        return (size_t)v.b * nbuf * pl->P.rmaxp * v.q * v.t * sizeof(double) + (size_t)v.b * 1024 <=
+        const size_t ctas = v.b > 1 ? v.b : 1;
+        return ctas * nbuf * pl->P.rmaxp * v.q * v.t * sizeof(double) + ctas * 1024 <=
                (size_t)pl->smem_optin + 1024;
     };
     for (const V &v : tab)

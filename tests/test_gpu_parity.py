@@ -726,3 +726,97 @@ def test_constant_bank_residency_across_plans_streams_and_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ------------------------------------------------------------------------------------------
+# 2-D grids on the FP64 tensor cores (spline2d_dmma_kernel / slider2d_dmma_kernel)
+# ------------------------------------------------------------------------------------------
+
+def test_dmma_2d_spline_matches_bank_evaluator_and_reference(monkeypatch):
+    """The tensor-core path for 2-D pieces against the constant-bank evaluator (PCB_NO_DMMA2D=1) on a
+    ragged batch with knot hits, node hits, mixed-piece row tiles and 5 outputs (two passes of 4),
+    and against the reference-made golden values."""
+    import pychebyshev_b200 as pcb
+
+    for name in ("spline_bs2d", "spline_nested2d"):
+        g, sp = _spline(name)
+        knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+        fac = G.spline_factor(g, knots, pieces)
+        got = sp.eval_batch_multi(g["points"], g["orders"])
+        for r, o in enumerate(g["orders"]):
+            scale_close(got[:, r], g["values"][:, r], f"{name} dmma2d order={o}", factor=fac)
+    g, sp = _spline("spline_bs2d")
+    rng = np.random.default_rng(99)
+    n = 128 * 37 + 51
+    pts = np.column_stack([rng.uniform(80.0, 120.0, n), rng.uniform(0.25, 1.0, n)])
+    pts[::7, 0] = 100.0                                    # on the knot: right piece
+    pts[3::11, 0] = sp._pieces[0].nodes[0][4]              # node hit in dim 0
+    pts[5::13, 1] = sp._pieces[1].nodes[1][9]              # node hit in dim 1
+    pts[:64, 0] = np.where(np.arange(64) % 2 == 0, 90.0, 110.0)  # alternate pieces inside row tiles
+    orders = [[0, 0], [1, 0], [0, 1], [2, 0], [1, 1]]
+    a = sp.eval_batch_multi(pts, orders)
+    pa = sp.find_pieces(pts)
+    monkeypatch.setenv("PCB_NO_DMMA2D", "1")
+    sp2 = pcb.ChebyshevSpline.from_values([p.tensor_values for p in sp._pieces], 2, sp.domain,
+                                          sp.n_nodes, sp.knots)
+    b = sp2.eval_batch_multi(pts, orders)
+    assert np.array_equal(pa, sp2.find_pieces(pts))
+    for r, o in enumerate(orders):
+        scale_close(a[:, r], b[:, r], f"dmma2d vs bank order={o}")
+
+
+def test_dmma_2d_slider_matches_bank_evaluator(monkeypatch):
+    import pychebyshev_b200 as pcb
+
+    g = G.load("slider10d")
+    part, pivot_value, slides = G.slider_parts(g, O.diff_matrix)
+    dom = [list(map(float, r)) for r in g["domain"]]
+    nn = [int(v) for v in g["n_nodes"]]
+
+    def make():
+        return pcb.ChebyshevSlider.from_slides([s[0] for s in slides], 10, dom, nn, part,
+                                               list(g["pivot_point"]), pivot_value)
+    rng = np.random.default_rng(7)
+    n = 128 * 9 + 77
+    pts = rng.uniform(80.0, 120.0, size=(n, 10))
+    pts[::9, 2] = slides[1][1][0][3]                       # node hit in slide 1, dim 0
+    orders = [[0] * 10, [1] + [0] * 9, [0] * 9 + [2], [1, 0, 1] + [0] * 7, [0, 1] + [0] * 8,
+              [0, 0, 0, 1] + [0] * 6]                      # 6 rows: > SLIDER_ACC
+    a = make().eval_batch_multi(pts, orders)
+    monkeypatch.setenv("PCB_NO_DMMA2D", "1")
+    b = make().eval_batch_multi(pts, orders)
+    assert (a[:, 3] == 0.0).all()
+    for r, o in enumerate(orders):
+        scale_close(a[:, r], b[:, r], f"slider dmma2d vs bank order={o}")
+
+
+# ------------------------------------------------------------------------------------------
+# full tensor: joint-K tensor-core variant (pcb_full_eval algo 3)
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["full_3d", "full_4d", "full_bs5d"])
+def test_full_joint_k_tensor_core_variant(name, monkeypatch):
+    """The DMMA GEMM over the last two axes jointly (K = n_d * n_e, A fragments in registers) against
+    the reference goldens and against the per-row tensor-core variant, ragged batch included."""
+    from pychebyshev_b200 import workloads as wl
+
+    monkeypatch.setenv("PCB_FORCE_DMMA2", "1")  # also where the planner would prefer the per-row variant
+    if name == "full_bs5d":
+        gg = G.load(name)
+        nodes = G.split(gg["nodes_cat"], [int(v) for v in gg["n_nodes"]])
+        g, cheb = _full(name, wl.grid_values(wl.bs_call_price, nodes))
+    else:
+        g, cheb = _full(name)
+    got = cheb.eval_batch_multi(g["points"], g["orders"], algo=3)
+    fac = _full_factor(g, cheb)
+    for r in range(got.shape[1]):
+        scale_close(got[:, r], g["values"][:, r], f"{name} joint-K order={g['orders'][r]}", factor=fac)
+    rng = np.random.default_rng(17)
+    dom = np.array(cheb.domain)
+    pts = rng.uniform(dom[:, 0], dom[:, 1], size=(128 * 5 + 37, cheb.num_dimensions))
+    pts[3] = [cheb.nodes[d][1] for d in range(cheb.num_dimensions)]  # node hits in every dim
+    orders = [list(map(int, o)) for o in g["orders"][:3]]
+    a = cheb.eval_batch_multi(pts, orders, algo=3)
+    b = cheb.eval_batch_multi(pts, orders, algo=2)
+    for r in range(len(orders)):
+        scale_close(a[:, r], b[:, r], f"{name} joint-K vs per-row order={orders[r]}")
