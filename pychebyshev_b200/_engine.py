@@ -34,6 +34,19 @@ def _torch():
     return torch
 
 
+def configure_host_pipeline(chunk_mb=None, ring_depth=None) -> dict:
+    """Chunk size (MB of input per chunk) and ring depth of the host-buffer pipeline; existing
+    per-device rings are dropped so the next call rebuilds them.  Returns the active settings."""
+    global _CHUNK_BYTES, _NBUF
+    if chunk_mb is not None:
+        _CHUNK_BYTES = max(1, int(chunk_mb)) << 20
+    if ring_depth is not None:
+        _NBUF = max(2, int(ring_depth))
+    with _HostPipe._guard:
+        _HostPipe._pipes.clear()
+    return {"chunk_mb": _CHUNK_BYTES >> 20, "ring_depth": _NBUF}
+
+
 def require_device(device=None) -> int:
     """Resolve ``device`` to a CUDA ordinal; raise loudly when there is none."""
     torch = _torch()

@@ -368,11 +368,11 @@ static int tt_launch_kernel(K kernel, const TTPlan *pl, const TTCfg &cfg, int64_
 // cores the generic one.  X(QPT, LC, MAXT)
 // (a launch with `threads` picks the first entry whose MAXT >= threads: keep MAXT ascending)
 #define TT_RESIDENT_CONFIGS(X) \
-    X(2, 8, 256) X(2, 12, 256) X(2, 16, 256) X(3, 12, 256) X(4, 12, 256) X(3, 12, 384) \
+    X(2, 8, 256) X(2, 12, 256) X(2, 16, 256) \
     X(1, 8, 512) X(1, 12, 512) X(1, 16, 512) X(2, 8, 512) X(2, 12, 512) X(2, 16, 512)
 #define TT_GENERIC_CONFIGS(X) X(2, 16, 256) X(1, 16, 512) X(2, 16, 512)
 #define TT_SHARED_RESIDENT_CONFIGS(X) \
-    X(2, 8, 256) X(2, 12, 256) X(2, 16, 256) X(3, 12, 256) \
+    X(2, 8, 256) X(2, 12, 256) X(2, 16, 256) \
     X(2, 8, 384) X(2, 12, 384) X(2, 16, 384) \
     X(1, 8, 512) X(1, 12, 512) X(1, 16, 512) X(2, 12, 512)
 

@@ -20,8 +20,7 @@ static bool tt_try_cfg(const TTPlan *pl, bool shared, int mode, int qpt, int thr
     const int nbuf = (shared ? 2 : 1) + pingpong;
     const size_t bytes = (size_t)tt_smem_doubles(P, mode, shared, nbuf, qpt, threads) * sizeof(double);
     if (bytes > (size_t)pl->smem_optin) return false;
-    // three/four query slots per thread are instantiated for the 12-wide resident case only
-    if (qpt >= 3 && !(mode == TT_RESIDENT && lc == 12)) return false;
+    if (qpt >= 3) return false;  // the shared-memory kernels are instantiated for 1 and 2 query slots
     c->qpt = qpt;
     c->threads = threads;
     c->lc = lc;
@@ -38,7 +37,7 @@ int tt_pick_cfg(const TTPlan *pl, bool shared, TTCfg *cfg) {
     // measured on B200 (tools/tt_sweep.py, 5D Black-Scholes TT, gpurun_out/tt_sweep3.log): chain
     // kernels 2 slots x 512 threads 3.06e9 values/s (3 x 256: 2.79e9, 1 x 512: 2.29e9);
     // shared-FD kernel 2 x 384 threads 1.26e9 q/s (2 x 512: 1.02e9, 3 x 256: 1.19e9)
-    static const int chain_pref[][2] = {{2, 512}, {3, 256}, {2, 256}, {1, 512}, {1, 256}};
+    static const int chain_pref[][2] = {{2, 512}, {2, 256}, {1, 512}, {1, 256}, {1, 128}};
     static const int shared_pref[][2] = {{2, 384}, {2, 256}, {1, 512}, {1, 256}, {1, 128}};
     for (int mode = TT_RESIDENT; mode <= TT_GLOBAL; ++mode) {
         if (force_q || force_t) {

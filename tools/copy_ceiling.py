@@ -81,7 +81,8 @@ def main():
         moved = (b_in if mode != "d2h" else 0) + (b_out if mode != "h2d" else 0)
         return moved / best / 1e9
 
-    for placement in ("default", "numa_local"):
+    quick = os.environ.get("COPY_QUICK") == "1"   # only: default placement, 64 MB chunks, both directions
+    for placement in (("default",) if quick else ("default", "numa_local")):
         if placement == "numa_local":
             bound = _numa.bind_thread(local)
             if not bound and world > 1 and rank != 0:
@@ -91,8 +92,8 @@ def main():
             h_out = torch.empty(b_out, dtype=torch.uint8, pin_memory=True)
             h_in[::4096] = 1
             h_out[::4096] = 1
-        for chunk_mb in (16, 64, 256):
-            for mode in ("h2d", "d2h", "both"):
+        for chunk_mb in ((64,) if quick else (16, 64, 256)):
+            for mode in (("both",) if quick else ("h2d", "d2h", "both")):
                 if chunk_mb != 64 and mode != "both":
                     continue
                 results[f"{placement}/{chunk_mb}MB/{mode}"] = measure(h_in, h_out, chunk_mb << 20, mode)
@@ -138,7 +139,8 @@ def main():
                 "affinity": sorted(os.sched_getaffinity(0)),
             }
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"copy_ceiling_N{world}.json"), "w") as f:
+        tag = f"_q{n // 1000000}M" if quick else ""
+        with open(os.path.join(ROOT, "gpurun_out", f"copy_ceiling_N{world}{tag}.json"), "w") as f:
             json.dump(doc, f, indent=1)
         print(json.dumps({k: doc[k] for k in doc if k != "topology"}))
     if world > 1:
