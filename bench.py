@@ -257,7 +257,8 @@ class SplineCase(Case):
                               "(6 ops per node + 1/sum per dim)")
             self.bytes_q = 8.0 * (dim + self.G)
             self.kernel = ("spline2d_dmma_kernel" if dim == 2 and not os.environ.get("PCB_NO_DMMA2D")
-                           else "spline_bank_kernel")
+                           else ("spline3d_dmma_kernel" if dim == 3 and not os.environ.get("PCB_NO_DMMA3D")
+                                 else "spline_bank_kernel"))
 
     def obj(self, dev):
         import pychebyshev_b200 as pcb
@@ -367,7 +368,7 @@ def make_case(key):
             cpu_rate=500.0),
         "full_c4": lambda: FullCase(
             "full_c4", "c4", "6D ChebyshevApproximation 16^6 (4 x 134 MB tensors): price+delta+"
-            "gamma+vega, queries sharded across the GPUs", "C4", 148 * 256 * 4, scaling="strong",
+            "gamma+vega, queries sharded across the GPUs", "C4", 148 * 256 * 8, scaling="strong",
             cpu_rate=3.0, cpu_procs=2),
         "spline2d_lookup": lambda: SplineCase(
             "spline2d_lookup", 2, None, "2D ChebyshevSpline, knot at the strike: piece lookup "

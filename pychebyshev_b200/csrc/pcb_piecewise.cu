@@ -55,8 +55,13 @@ struct SplinePlan : PlanBase {
     // 2-D splines on the FP64 tensor cores: piece tensors in MMA fragment order [piece][output]
     bool dmma2d_ok = false;
     double *d_frags = nullptr;
+    // 3-D splines on the tensor cores (joint-K): fragment images + (j, kz) index tables per piece
+    bool dmma3d_ok = false;
+    int kb3max = 0, g3_per = 1;  // K blocks of the largest piece; outputs per launch
+    int *d_tabs = nullptr;
     ~SplinePlan() override;
     void free_all() {
+        if (d_tabs) cudaFree(d_tabs);
         if (d_frags) cudaFree(d_frags);
         if (d_num_knots) cudaFree(d_num_knots);
         if (d_knots) cudaFree(d_knots);
@@ -811,6 +816,175 @@ slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ 
         if (live && g < G) o[g] = acc[g];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 3-D spline pieces on the FP64 tensor cores: the last two axes jointly on the MMA K dimension.
+//     p(x, y, z) = sum_i a_i  sum_{(j,k)} (b_j c_k) T[i][(j,k)]
+// For 8 queries: U[q, i] = A[q, (j,k)] B[(j,k), i],  A = b_j(q) c_k(q) built on the fly (two
+// tile reads + one DMUL per fragment element, indices from a per-piece table in shared memory),
+// B = the piece's tensor in fragment order (shared memory), K = n1 n2 padded to 4, N = n0 padded
+// to 8; then the dot with a(x): 4 FMA per lane and a quad shuffle.  15^3: 114 DMMA per 8 queries
+// replace 3,600 DFMA per query-thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int BL3_THREADS = 256;                     // 8 warps share one staged copy of the fragments
+constexpr int BL3_MAX_KB = 64;                       // n1 * n2 <= 256
+constexpr int BL3_WARP_DOUBLES = 3 * 16 * BL_SA + BL_OUT * 32 + 32;  // three weight tiles, outputs, scratch
+
+// one 8-query row tile against one piece: frag = [KB][NT = 2][32] per output, tab[k] = (j, kz) packed
+template <int NT>
+__device__ __forceinline__ void bl3_tile_n(int KB, int fragstride, const double *frag, const int *tab,
+                                           int o0, int no, int t, const double *sA, const double *sB,
+                                           const double *sC, double *sOut, int lane, bool take) {
+    const int r = lane >> 2, c = lane & 3;
+    const int q = 8 * t + r;
+    double aq[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) aq[nt][e] = sA[(8 * nt + 2 * c + e) * BL_SA + q];
+    for (int o = 0; o < no; ++o) {
+        const double *f = frag + (size_t)(o0 + o) * fragstride + lane;
+        double acc[NT][2], accb[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = accb[nt][0] = accb[nt][1] = 0.0;
+#pragma unroll 2
+        for (int kb = 0; kb < KB; ++kb) {
+            const int jk = tab[4 * kb + c];  // (j << 16) | kz; padding rows point at a zero entry
+            const double a = sB[(jk >> 16) * BL_SA + q] * sC[(jk & 0xffff) * BL_SA + q];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b = f[(kb * 2 + nt) * 32];
+                if (kb & 1)
+                    bl_dmma(accb[nt][0], accb[nt][1], a, b);
+                else
+                    bl_dmma(acc[nt][0], acc[nt][1], a, b);
+            }
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            part = fma(acc[nt][0] + accb[nt][0], aq[nt][0], part);
+            part = fma(acc[nt][1] + accb[nt][1], aq[nt][1], part);
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (c == 0 && take) sOut[o * 32 + q] = part;
+    }
+}
+
+// One launch evaluates outputs [g0, g0 + G) of Gtot (the fragment images of all outputs of a launch
+// must fit in shared memory next to the per-warp tiles).
+__global__ void __launch_bounds__(BL3_THREADS)
+spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__restrict__ num_knots,
+                     const int *__restrict__ knot_off, const double *__restrict__ knots,
+                     const double *__restrict__ frags, const int *__restrict__ tabs,
+                     const double *__restrict__ pts, int64_t N, double *__restrict__ out,
+                     int32_t *__restrict__ piece_out) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_cnt[BANK_GRIDS];
+    __shared__ unsigned short s_perm[BL3_THREADS];
+    __shared__ unsigned char s_piece[BL3_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fragstride = KBmax * 64;                       // doubles per (piece, output)
+    double *sFrag = smem;
+    int *sTab = reinterpret_cast<int *>(smem + (size_t)P * G * fragstride);  // [P][KBmax * 4]
+    double *sA = smem + (size_t)P * G * fragstride + ((size_t)P * KBmax * 4 + 1) / 2 + warp * BL3_WARP_DOUBLES;
+    double *sB = sA + 16 * BL_SA;
+    double *sC = sB + 16 * BL_SA;
+    double *sOut = sC + 16 * BL_SA;
+    const int64_t q0 = (int64_t)blockIdx.x * BL3_THREADS;
+    for (int pg = 0; pg < P * G; ++pg) {  // image of (piece p, output g0 + o) -> slot p * G + o
+        const double *src = frags + (size_t)((pg / G) * Gtot + g0 + pg % G) * fragstride;
+        for (int e = tid; e < fragstride; e += BL3_THREADS) sFrag[(size_t)pg * fragstride + e] = __ldg(src + e);
+    }
+    for (int e = tid; e < P * KBmax * 4; e += BL3_THREADS) sTab[e] = __ldg(tabs + e);
+    int mine;
+    {
+        const int64_t ql = q0 + tid < N ? q0 + tid : N - 1;
+        mine = spline_piece_index(3, num_knots, knot_off, knots, pts + ql * 3);
+        if (piece_out && q0 + tid < N) piece_out[q0 + tid] = mine;
+    }
+    if (tid < BANK_GRIDS) s_cnt[tid] = 0;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, mine);
+    const int leader = __ffs(peers) - 1;
+    int warp_off = 0;
+    if (lane == leader) warp_off = atomicAdd(&s_cnt[mine], __popc(peers));
+    warp_off = __shfl_sync(0xffffffffu, warp_off, leader);
+    __syncthreads();
+    int pos = warp_off + __popc(peers & ((1u << lane) - 1u));
+    for (int p = 0; p < P; ++p) pos += p < mine ? s_cnt[p] : 0;
+    s_perm[pos] = (unsigned short)tid;
+    s_piece[pos] = (unsigned char)mine;
+    __syncthreads();
+    mine = s_piece[tid];
+    const int64_t q = q0 + s_perm[tid];
+    const bool live = q < N;
+    const double *x = pts + (live ? q : N - 1) * 3;
+    double *o = out + (live ? q : N - 1) * Gtot + g0;
+    // 1. weight rows of the three dims (entry 15 of every tile row set stays zero-padded by mode 2)
+    const unsigned present = __reduce_or_sync(0xffffffffu, 1u << mine);
+    double inv = 1.0;
+    for (int p = 0; p < P; ++p) {
+        if (!((present >> p) & 1u)) continue;
+        const BankGrid &g = c_bgrid[p];
+        const bool keep = mine == p;
+        double row[GRID_NL];
+        double *dump = sOut + BL_OUT * 32;
+        const double sa = bank_row<2>(__ldg(x + 0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
+                                      __double_as_longlong(c_grid[g.scale_off + 3 + 0]), row,
+                                      (keep ? sA : dump) + lane, keep ? BL_SA : 0, 1.0);
+        const double sb = bank_row<2>(__ldg(x + 1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
+                                      g.weight_off + g.n[0],
+                                      __double_as_longlong(c_grid[g.scale_off + 3 + 1]), row,
+                                      (keep ? sB : dump) + lane, keep ? BL_SA : 0, 1.0);
+        const double sc = bank_row<2>(__ldg(x + 2) * c_grid[g.scale_off + 2], g.n[2],
+                                      g.node_off + g.n[0] + g.n[1], g.weight_off + g.n[0] + g.n[1],
+                                      __double_as_longlong(c_grid[g.scale_off + 3 + 2]), row,
+                                      (keep ? sC : dump) + lane, keep ? BL_SA : 0, 1.0);
+        const double v = bank_rcp(sa * sb * sc);
+        if (keep) inv = v;
+    }
+    __syncwarp();
+    for (int o0 = 0; o0 < G; o0 += BL_OUT) {
+        const int no = G - o0 < BL_OUT ? G - o0 : BL_OUT;
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+            const int prow = __shfl_sync(0xffffffffu, mine, 8 * t + (lane >> 2));
+            const unsigned here = __reduce_or_sync(0xffffffffu, 1u << prow);
+            for (int p = 0; p < P; ++p) {
+                if (!((here >> p) & 1u)) continue;
+                const BankGrid &g = c_bgrid[p];
+                const int KB = (g.n[1] * g.n[2] + 3) >> 2;
+                const double *frag = sFrag + (size_t)p * G * fragstride;
+                const int *tab = sTab + p * KBmax * 4;
+                if (g.n[0] > 8)
+                    bl3_tile_n<2>(KB, fragstride, frag, tab, o0, no, t, sA, sB, sC, sOut, lane, prow == p);
+                else
+                    bl3_tile_n<1>(KB, fragstride, frag, tab, o0, no, t, sA, sB, sC, sOut, lane, prow == p);
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < no; ++k) {
+            const double v = sOut[k * 32 + lane] * inv;
+            if (live) o[o0 + k] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// Fragment image of one n0 x n1 x n2 tensor for the joint-K 3-D kernel:
+//   f[(kb * 2 + nt) * 32 + lane] = T[i = 8 nt + lane / 4][(j, kz) = 4 kb + lane % 4]
+static void bl3_make_frag(const double *t, int n0, int n1, int n2, int KBmax, double *f) {
+    const int K = n1 * n2;
+    for (int kb = 0; kb < KBmax; ++kb)
+        for (int nt = 0; nt < 2; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int i = 8 * nt + lane / 4, k = 4 * kb + lane % 4;
+                f[(kb * 2 + nt) * 32 + lane] = (i < n0 && k < K) ? t[(size_t)i * K + k] : 0.0;
+            }
+}
+
 // Fragment image of one n0 x n1 tensor: f[(kb * 2 + nt) * 32 + lane] = T[4 kb + lane % 4][8 nt + lane / 4]
 static void bl_make_frag(const double *t, int n0, int n1, double *f) {
     for (int kb = 0; kb < 4; ++kb)
@@ -1080,6 +1254,40 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
             if (!pl->dmma2d_ok) cudaGetLastError();
         }
     }
+    // 3-D pieces of at most 16 nodes per dim: joint-K tensor-core path
+    if (D == 3 && pl->bank_ok && P <= BANK_GRIDS && !getenv("PCB_NO_DMMA3D")) {
+        bool fits = true;
+        int kbmax = 1;
+        for (int p = 0; p < P; ++p) {
+            fits = fits && desc[p].n[0] <= 16 && desc[p].n[1] <= 16 && desc[p].n[2] <= 16;
+            kbmax = std::max(kbmax, (desc[p].n[1] * desc[p].n[2] + 3) / 4);
+        }
+        const size_t fragstride = (size_t)kbmax * 64;
+        // outputs per launch: as many as fit in shared memory next to the tiles of 8 warps
+        int per = 0;
+        for (int gl = G; gl >= 1 && !per; --gl) {
+            const size_t bytes = (size_t)P * gl * fragstride * 8 + (((size_t)P * kbmax * 4 + 1) / 2) * 8 +
+                                 (size_t)(BL3_THREADS / 32) * BL3_WARP_DOUBLES * 8;
+            if (bytes + 2048 <= (size_t)pl->smem_optin) per = gl;
+        }
+        if (fits && kbmax <= BL3_MAX_KB && per >= 1) {
+            pl->g3_per = per;
+            std::vector<double> fr((size_t)P * G * fragstride, 0.0);
+            std::vector<int> tabs((size_t)P * kbmax * 4, 0);
+            for (int p = 0; p < P; ++p) {
+                const int n1 = desc[p].n[1], n2 = desc[p].n[2], K = n1 * n2;
+                for (int g = 0; g < G; ++g)
+                    bl3_make_frag(piece_tensors_host[(size_t)p * G + g], desc[p].n[0], n1, n2, kbmax,
+                                  fr.data() + ((size_t)p * G + g) * fragstride);
+                for (int k = 0; k < kbmax * 4; ++k)  // rows beyond K: entry 15 of both tiles, which is zero
+                    tabs[(size_t)p * kbmax * 4 + k] = k < K ? ((k / n2) << 16) | (k % n2) : (15 << 16) | 15;
+                // (a 16-node dim has no zero entry 15: its padding rows meet zero B fragments instead)
+            }
+            pl->kb3max = kbmax;
+            pl->dmma3d_ok = upload(&pl->d_frags, fr.data(), fr.size()) && upload(&pl->d_tabs, tabs.data(), tabs.size());
+            if (!pl->dmma3d_ok) cudaGetLastError();
+        }
+    }
     *plan = pl;
     return PCB_OK;
 }
@@ -1121,6 +1329,24 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
                          (void *)&d_out, (void *)&d_piece};
         return bank_launch(pl, part.id, part.h_bank, part.h_desc, (const void *)spline2d_dmma_kernel, dargs,
                            dsm, N, static_cast<cudaStream_t>(stream), BL_THREADS);
+    }
+    if (pl->dmma3d_ok) {
+        const SplinePlan::BankPart &part = pl->parts[0];
+        const size_t fragstride = (size_t)pl->kb3max * 64;
+        for (int g0 = 0; g0 < pl->G; g0 += pl->g3_per) {
+            int gl = std::min(pl->g3_per, pl->G - g0);
+            const size_t dsm = ((size_t)pl->P * gl * fragstride + ((size_t)pl->P * pl->kb3max * 4 + 1) / 2 +
+                                (size_t)(BL3_THREADS / 32) * BL3_WARP_DOUBLES) * sizeof(double);
+            int32_t *piece = g0 == 0 ? d_piece : nullptr;
+            void *dargs[] = {(void *)&gl, (void *)&g0, (void *)&pl->G, (void *)&pl->P, (void *)&pl->kb3max,
+                             (void *)&pl->d_num_knots, (void *)&pl->d_knot_off, (void *)&pl->d_knots,
+                             (void *)&pl->d_frags, (void *)&pl->d_tabs, (void *)&d_points, (void *)&N,
+                             (void *)&d_out, (void *)&piece};
+            if (int rc = bank_launch(pl, part.id, part.h_bank, part.h_desc, (const void *)spline3d_dmma_kernel,
+                                     dargs, dsm, N, static_cast<cudaStream_t>(stream), BL3_THREADS))
+                return rc;
+        }
+        return PCB_OK;
     }
     if (pl->bank_ok) {
         for (const SplinePlan::BankPart &part : pl->parts) {

@@ -820,3 +820,36 @@ def test_full_joint_k_tensor_core_variant(name, monkeypatch):
     b = cheb.eval_batch_multi(pts, orders, algo=2)
     for r in range(len(orders)):
         scale_close(a[:, r], b[:, r], f"{name} joint-K vs per-row order={orders[r]}")
+
+
+def test_dmma_3d_spline_matches_bank_evaluator_and_reference(monkeypatch):
+    """3-D pieces on the tensor cores (joint-K over the last two axes) against the reference goldens
+    and the constant-bank evaluator (PCB_NO_DMMA3D=1): ragged batch, knot / node hits, mixed-piece row
+    tiles, several outputs (split over launches when the fragment images do not fit together)."""
+    import pychebyshev_b200 as pcb
+
+    for name in ("spline_bs3d", "spline_multiknot3d"):
+        g, sp = _spline(name)
+        knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+        fac = G.spline_factor(g, knots, pieces)
+        got = sp.eval_batch_multi(g["points"], g["orders"])
+        for r, o in enumerate(g["orders"]):
+            scale_close(got[:, r], g["values"][:, r], f"{name} dmma3d order={o}", factor=fac)
+    g, sp = _spline("spline_bs3d")
+    rng = np.random.default_rng(123)
+    n = 256 * 11 + 77
+    pts = np.column_stack([rng.uniform(80.0, 120.0, n), rng.uniform(0.25, 1.0, n), rng.uniform(0.01, 0.08, n)])
+    pts[::7, 0] = 100.0
+    pts[3::11, 0] = sp._pieces[0].nodes[0][4]
+    pts[5::13, 2] = sp._pieces[1].nodes[2][9]
+    pts[:64, 0] = np.where(np.arange(64) % 2 == 0, 90.0, 110.0)
+    orders = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 2], [1, 0, 1]]
+    a = sp.eval_batch_multi(pts, orders)
+    pa = sp.find_pieces(pts)
+    monkeypatch.setenv("PCB_NO_DMMA3D", "1")
+    sp2 = pcb.ChebyshevSpline.from_values([p.tensor_values for p in sp._pieces], 3, sp.domain,
+                                          sp.n_nodes, sp.knots)
+    b = sp2.eval_batch_multi(pts, orders)
+    assert np.array_equal(pa, sp2.find_pieces(pts))
+    for r, o in enumerate(orders):
+        scale_close(a[:, r], b[:, r], f"dmma3d vs bank order={o}")

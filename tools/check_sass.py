@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pychebyshev_b200", "libpcb_b200.so")
 
 PATTERNS = ("ttc_value_kernel", "ttc_fd_shared_kernel", "ttc_gstep_kernel", "ttc_gcoeff_kernel",
-            "spline_bank_kernel", "slider_bank_kernel", "spline2d_dmma_kernel", "slider2d_dmma_kernel")
+            "spline_bank_kernel", "slider_bank_kernel", "spline2d_dmma_kernel", "slider2d_dmma_kernel",
+            "spline3d_dmma_kernel")
 
 #: kernels the planner selects by default (pcb_tt_const.cu kValueVariants / kSharedVariants first
 #: entries per rank class, the per-core step kernel, the bank evaluators the benchmark configurations
@@ -32,7 +33,7 @@ MUST_BE_UNIFORM = (
     "spline_bank_kernel<1, 2>", "spline_bank_kernel<2, 2>", "spline_bank_kernel<2, 3>",
     "spline_bank_kernel<4, 2>", "spline_bank_kernel<4, 3>", "spline_bank_kernel<4, 4>",
     "slider_bank_kernel<1, 2>", "slider_bank_kernel<2, 2>", "slider_bank_kernel<4, 2>",
-    "spline2d_dmma_kernel", "slider2d_dmma_kernel",
+    "spline2d_dmma_kernel", "slider2d_dmma_kernel", "spline3d_dmma_kernel",
 )
 #: at most this share of a MUST_BE_UNIFORM kernel's bank reads may be per-lane (descriptor fields
 #: that feed per-lane predicates are legitimately read with LDC)

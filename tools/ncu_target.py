@@ -43,13 +43,13 @@ def main():
             orders = wl.BS5D_GREEKS if name == "tt_bs5d" else g["fd_orders"][:3]
             algo = 1 if which == "tt_fd1" else 2
             fn = lambda: tt.eval_multi_batch(pts, orders, algo=algo)  # noqa: E731
-    elif which in ("full_dmma", "full_fma"):
+    elif which in ("full_dmma", "full_fma", "full_dmma2"):
         g = G.load("full_bs5d")
         nodes = G.split(g["nodes_cat"], [int(v) for v in g["n_nodes"]])
         tensor = wl.grid_values(wl.bs_call_price, nodes)
         cheb = pcb.ChebyshevApproximation.from_values(tensor, 5, wl.BS5D_DOMAIN, wl.BS5D_NODES)
-        algo = 2 if which == "full_dmma" else 1
-        n = n or (148 * 256 if algo == 2 else 20000)
+        algo = {"full_dmma": 2, "full_dmma2": 3}.get(which, 1)
+        n = n or (148 * 256 if algo >= 2 else 20000)
         pts = rand_points(wl.BS5D_DOMAIN, n)
         fn = lambda: cheb.eval_batch_multi(pts, wl.BS5D_GREEKS, algo=algo)  # noqa: E731
     elif which == "slider":
