@@ -89,3 +89,18 @@ def normalize_orders(orders, ndim: int) -> tuple:
             raise ValueError("derivative orders must be non-negative")
         out.append(o)
     return tuple(out)
+
+
+def point_row(point, ndim: int) -> np.ndarray:
+    """One query as a ``(1, ndim)`` float64 array, read the way the reference's single-point methods
+    read it: ``point[d]`` for ``d < ndim`` only (longer sequences are tolerated), and a length-1
+    sequence counts as its element (NumPy broadcasting makes ``[0.1] - nodes`` equal ``0.1 - nodes``
+    there; the reference's own tests pass such points, tests/test_from_values.py:246-254)."""
+    row = np.empty((1, ndim), dtype=np.float64)
+    for d in range(ndim):
+        v = np.asarray(point[d], dtype=np.float64)
+        if v.size != 1:
+            raise ValueError(f"point[{d}] must be a scalar, got shape {v.shape}")
+        row[0, d] = v.reshape(-1)[0]
+    return row
+

@@ -398,14 +398,14 @@ class ChebyshevApproximation(_DerivativeIds):
         order = self._resolve_derivative_args(derivative_order, derivative_id)
         if self.tensor_values is None:
             raise RuntimeError("Call build() first")
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return float(self._plan([order]).eval(pts)[0, 0])
 
     def vectorized_eval_multi(self, point, derivative_orders) -> List[float]:
         """Single point, several derivative orders (reference ``barycentric.py:1049-1112``)."""
         if self.tensor_values is None:
             raise RuntimeError("Call build() first")
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return [float(v) for v in self._plan(derivative_orders).eval(pts)[0]]
 
     # the reference's scalar-loop variants return the same interpolant value

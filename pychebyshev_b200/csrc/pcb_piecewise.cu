@@ -673,6 +673,106 @@ __device__ __forceinline__ void bl_tile(const BankGrid &g, const double *frag, i
     }
 }
 
+// All four row tiles of a single-grid warp at once (2-D): each B fragment is loaded once for four
+// DMMAs and eight accumulator chains are in flight.
+template <int KB, int NT>
+__device__ __forceinline__ void bl_tiles2_n(const double *frag, int o0, int no, int t0, const double *sA,
+                                            const double *sB, double *sOut, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    double af[KB][2];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) af[kb][t] = sA[(4 * kb + c) * BL_SA + 8 * (t0 + t) + r];
+    for (int o = 0; o < no; ++o) {
+        const double *f = frag + (size_t)(o0 + o) * BL_FRAG + lane;
+        double acc[2][NT][2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b = f[(kb * 2 + nt) * 32];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) bl_dmma(acc[t][nt][0], acc[t][nt][1], af[kb][t], b);
+            }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            double part = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                part = fma(acc[t][nt][0], sB[(8 * nt + 2 * c) * BL_SB + 8 * (t0 + t) + r], part);
+                part = fma(acc[t][nt][1], sB[(8 * nt + 2 * c + 1) * BL_SB + 8 * (t0 + t) + r], part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (c == 0) sOut[o * 32 + 8 * (t0 + t) + r] = part;
+        }
+    }
+}
+#define BL_TILES2_CASE(KBV, NTV) \
+    case (KBV) * 2 + (NTV): bl_tiles2_n<KBV, NTV>(frag, o0, no, t0, sA, sB, sOut, lane); break;
+__device__ __forceinline__ void bl_tiles2(const BankGrid &g, const double *frag, int o0, int no, int t0,
+                                          const double *sA, const double *sB, double *sOut, int lane) {
+    switch (((g.n[0] + 3) >> 2) * 2 + ((g.n[1] + 7) >> 3)) {
+        BL_TILES2_CASE(1, 1) BL_TILES2_CASE(1, 2) BL_TILES2_CASE(2, 1) BL_TILES2_CASE(2, 2)
+        BL_TILES2_CASE(3, 1) BL_TILES2_CASE(3, 2) BL_TILES2_CASE(4, 1) BL_TILES2_CASE(4, 2)
+    }
+}
+
+template <int KB, int NT>
+__device__ __forceinline__ void bl_tiles4_n(const double *frag, int o0, int no, const double *sA,
+                                            const double *sB, double *sOut, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    double af[KB][4];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) af[kb][t] = sA[(4 * kb + c) * BL_SA + 8 * t + r];
+    for (int o = 0; o < no; ++o) {
+        const double *f = frag + (size_t)(o0 + o) * BL_FRAG + lane;
+        double acc[4][NT][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b = f[(kb * 2 + nt) * 32];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) bl_dmma(acc[t][nt][0], acc[t][nt][1], af[kb][t], b);
+            }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            double part = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                part = fma(acc[t][nt][0], sB[(8 * nt + 2 * c) * BL_SB + 8 * t + r], part);
+                part = fma(acc[t][nt][1], sB[(8 * nt + 2 * c + 1) * BL_SB + 8 * t + r], part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (c == 0) sOut[o * 32 + 8 * t + r] = part;
+        }
+    }
+}
+
+#define BL_TILES4_CASE(KBV, NTV) \
+    case (KBV) * 2 + (NTV): bl_tiles4_n<KBV, NTV>(frag, o0, no, sA, sB, sOut, lane); break;
+
+__device__ __forceinline__ void bl_tiles4(const BankGrid &g, const double *frag, int o0, int no,
+                                          const double *sA, const double *sB, double *sOut, int lane) {
+    switch (((g.n[0] + 3) >> 2) * 2 + ((g.n[1] + 7) >> 3)) {
+        BL_TILES4_CASE(1, 1) BL_TILES4_CASE(1, 2) BL_TILES4_CASE(2, 1) BL_TILES4_CASE(2, 2)
+        BL_TILES4_CASE(3, 1) BL_TILES4_CASE(3, 2) BL_TILES4_CASE(4, 1) BL_TILES4_CASE(4, 2)
+    }
+}
+
 __device__ __forceinline__ void bl_stage_frags(double *sFrag, const double *__restrict__ frags, int nfrag) {
     for (int e = threadIdx.x; e < nfrag * BL_FRAG; e += BL_THREADS) sFrag[e] = __ldg(frags + e);
 }
@@ -730,14 +830,21 @@ spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int 
     // 2. + 3. row tiles x pieces present in the tile, BL_OUT outputs per pass
     for (int o0 = 0; o0 < G; o0 += BL_OUT) {
         const int no = G - o0 < BL_OUT ? G - o0 : BL_OUT;
+        if ((present & (present - 1u)) == 0u) {
+            const int p = __ffs(present) - 1;
 #pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
-            const int prow = __shfl_sync(0xffffffffu, mine, 8 * t + (lane >> 2));
-            const unsigned here = __reduce_or_sync(0xffffffffu, 1u << prow);
-            for (int p = 0; p < P; ++p) {
-                if (!((here >> p) & 1u)) continue;
-                bl_tile(c_bgrid[p], sFrag + (size_t)p * G * BL_FRAG, o0, no, t, sA, sB, sOut, lane,
-                        prow == p);
+            for (int t0 = 0; t0 < 4; t0 += 2)
+                bl_tiles2(c_bgrid[p], sFrag + (size_t)p * G * BL_FRAG, o0, no, t0, sA, sB, sOut, lane);
+        } else {
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                const int prow = __shfl_sync(0xffffffffu, mine, 8 * t + (lane >> 2));
+                const unsigned here = __reduce_or_sync(0xffffffffu, 1u << prow);
+                for (int p = 0; p < P; ++p) {
+                    if (!((here >> p) & 1u)) continue;
+                    bl_tile(c_bgrid[p], sFrag + (size_t)p * G * BL_FRAG, o0, no, t, sA, sB, sOut, lane,
+                            prow == p);
+                }
             }
         }
         __syncwarp();
@@ -751,7 +858,11 @@ spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int 
 
 // Slider of 2-D slides: value rows accumulate pivot + sum_s (slide_s - pivot) left to right
 // (slider.py:310-318), a derivative row takes its slide's output, cross-slide rows are exactly 0.
-__global__ void __launch_bounds__(BL_THREADS)
+// All four row tiles of a warp are multiplied at once (bl_tiles4).  (minBlocks = 6 is an 80-register
+// budget: with the four-tile routine ptxas keeps the bank reads on the uniform datapath at 80
+// registers and drops them at the unbounded 94; the same routine takes spline2d_dmma_kernel off the
+// uniform path at any budget, so that kernel multiplies tile by tile.  tools/check_sass.py)
+__global__ void __launch_bounds__(BL_THREADS, 6)
 slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ out_slide,
                      const int *__restrict__ row_out, const int *__restrict__ frag_off, int nfrag,
                      const double *__restrict__ frags, const double *__restrict__ pts, int64_t N,
@@ -781,9 +892,7 @@ slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ 
         __syncwarp();
         for (int o0 = 0; o0 < sg; o0 += BL_OUT) {
             const int no = sg - o0 < BL_OUT ? sg - o0 : BL_OUT;
-#pragma unroll 1
-            for (int t = 0; t < 4; ++t)
-                bl_tile(gr, sFrag + (size_t)frag_off[s] * BL_FRAG, o0, no, t, sA, sB, sOut, lane, true);
+            bl_tiles4(gr, sFrag + (size_t)frag_off[s] * BL_FRAG, o0, no, sA, sB, sOut, lane);
             __syncwarp();
             for (int k = 0; k < no; ++k) {
                 const int so = o0 + k;
@@ -948,6 +1057,9 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
     __syncwarp();
     for (int o0 = 0; o0 < G; o0 += BL_OUT) {
         const int no = G - o0 < BL_OUT ? G - o0 : BL_OUT;
+        // (multiplying all four row tiles at once -- one B-fragment load per four DMMAs -- measured
+        // 6 % SLOWER here, 1.63e9 against 1.73e9 q/s: the on-the-fly A fragments of four tiles crowd the
+        // same shared-memory pipe; the slider's 2-D slides gain 12 % from it)
 #pragma unroll 1
         for (int t = 0; t < 4; ++t) {
             const int prow = __shfl_sync(0xffffffffu, mine, 8 * t + (lane >> 2));

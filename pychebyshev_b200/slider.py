@@ -140,14 +140,14 @@ class ChebyshevSlider(_DerivativeIds):
         if not self._built:
             raise RuntimeError("Call build() before eval().")
         order = self._resolve_derivative_args(derivative_order, derivative_id)
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return float(self._plan([order]).eval(pts)[0, 0])
 
     def eval_multi(self, point, derivative_orders) -> List[float]:
         """Single point, several derivative orders (reference ``slider.py:320-337``)."""
         if not self._built:
             raise RuntimeError("Call build() before eval().")
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return [float(v) for v in self._plan(derivative_orders).eval(pts)[0]]
 
     # ------------------------------------------------------------------ persistence

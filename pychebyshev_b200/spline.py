@@ -253,7 +253,7 @@ class ChebyshevSpline(_DerivativeIds):
         return self._plan([[0] * self.num_dimensions], device).lookup(points)
 
     def _find_piece(self, point):
-        flat = int(self.find_pieces(np.asarray([list(point)], dtype=np.float64))[0])
+        flat = int(self.find_pieces(_grid.point_row(point, self.num_dimensions))[0])
         return flat, self._pieces[flat]
 
     def _check_knot_boundary(self, point, derivative_order) -> None:
@@ -293,7 +293,7 @@ class ChebyshevSpline(_DerivativeIds):
             raise RuntimeError("Call build() before eval().")
         order = self._resolve_derivative_args(derivative_order, derivative_id)
         self._check_knot_boundary(point, order)
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return float(self._plan([order]).eval(pts)[0, 0])
 
     def eval_multi(self, point, derivative_orders) -> List[float]:
@@ -302,7 +302,7 @@ class ChebyshevSpline(_DerivativeIds):
             raise RuntimeError("Call build() before eval_multi().")
         for o in derivative_orders:
             self._check_knot_boundary(point, o)
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return [float(v) for v in self._plan(derivative_orders).eval(pts)[0]]
 
     # ------------------------------------------------------------------ persistence

@@ -237,7 +237,7 @@ class ChebyshevTT:
 
     def eval(self, point) -> float:
         """Single point (reference ``tensor_train.py:2127-2170``)."""
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return float(self._plan().eval(pts)[0, 0])
 
     #: limits of ONE ``pcb_tt_eval_fd`` call (include/pcb_b200.h); larger row sets are split here
@@ -335,7 +335,7 @@ class ChebyshevTT:
     def eval_multi(self, point, derivative_orders) -> List[float]:
         """Value and central finite-difference derivatives at one point (reference
         ``tensor_train.py:2267-2320``)."""
-        pts = np.asarray([list(point)], dtype=np.float64)
+        pts = _grid.point_row(point, self.num_dimensions)
         return [float(v) for v in self.eval_multi_batch(pts, derivative_orders)[0]]
 
     # ------------------------------------------------------------------ grid evaluation (N4)

@@ -201,3 +201,15 @@ def test_tt_cross_build_accuracy():
     again = pcb.ChebyshevTT(wl.bs5d_scalar, 5, wl.BS5D_DOMAIN, wl.BS5D_NODES, max_rank=15, max_sweeps=5)
     again.build(verbose=False, seed=42)
     assert all(np.array_equal(a, b) for a, b in zip(tt._coeff_cores, again._coeff_cores))
+
+
+def test_single_point_coordinates_are_read_like_the_reference_reads_them():
+    """point[d] for d < D only; a length-1 sequence counts as its element (the reference's own
+    tests pass such points: tests/test_from_values.py:246-254)."""
+    assert np.array_equal(_grid.point_row([[0.1], [0.5], [0.9]], 1), [[0.1]])
+    assert np.array_equal(_grid.point_row((1.0, 2.0, 3.0, 4.0), 2), [[1.0, 2.0]])
+    assert np.array_equal(_grid.point_row(np.array([1, 2, 3]), 3), [[1.0, 2.0, 3.0]])
+    with pytest.raises(ValueError, match="scalar"):
+        _grid.point_row([[0.1, 0.2]], 1)
+    with pytest.raises(IndexError):
+        _grid.point_row([0.1], 2)
