@@ -594,7 +594,7 @@ constexpr int BL_THREADS = 128;                 // 4 warps; ~10 KB of tiles per 
 constexpr int BL_SA = 36, BL_SB = 34;           // padded strides (doubles) of the weight tiles
 constexpr int BL_FRAG = 256;                    // doubles per (grid, output): 4 k-blocks x 2 n-tiles x 32 lanes
 constexpr int BL_MAX_FRAGS = 24;                // staged in shared memory (48 KB)
-constexpr int BL_OUT = 4;                       // outputs folded per pass
+constexpr int BL_OUT = 2;                       // outputs folded per pass (2: five 128-thread CTAs fit in an SM)
 constexpr int BL_WARP_DOUBLES = 16 * BL_SA + 16 * BL_SB + BL_OUT * 32 + 32;  // tiles, outputs, scratch row
 
 __device__ __forceinline__ void bl_dmma(double &c0, double &c1, double a, double b) {

@@ -89,6 +89,27 @@ def kernel(rep, out):
                     "| opcode | executed | share | samples share |\n|---|---|---|---|\n")
             for op, n in ops.most_common(10):
                 f.write(f"| {op} | {n} | {100 * n / tot_i:.1f}% | {100 * samples[op] / tot_s:.1f}% |\n")
+            # where in the kernel the stall samples fall: 20 equal bins of the SASS listing (program
+            # order), and the 12 hottest instructions
+            body = [(r[si], int(r[ni] or 0), int(r[xi] or 0)) for r in srows[2:]
+                    if len(r) > max(si, ni, xi) and r[si].split() and (r[xi] or '0').isdigit()
+                    and (r[ni] or '0').isdigit()]
+            if body:
+                nb = 20
+                f.write("\nstall samples along the SASS listing (20 bins in program order):\n\n"
+                        "| bin | instructions | executed share | samples share | most sampled instruction |\n"
+                        "|---|---|---|---|---|\n")
+                per = max(1, (len(body) + nb - 1) // nb)
+                for b in range(0, len(body), per):
+                    chunk = body[b:b + per]
+                    hot = max(chunk, key=lambda t: t[1])
+                    f.write(f"| {b // per} | {b}-{b + len(chunk) - 1} | "
+                            f"{100 * sum(t[2] for t in chunk) / tot_i:.1f}% | "
+                            f"{100 * sum(t[1] for t in chunk) / tot_s:.1f}% | `{hot[0][:70]}` |\n")
+                f.write("\nhottest instructions:\n\n| # | samples share | executed | SASS |\n|---|---|---|---|\n")
+                order = sorted(range(len(body)), key=lambda i: -body[i][1])[:12]
+                for i in order:
+                    f.write(f"| {i} | {100 * body[i][1] / tot_s:.1f}% | {body[i][2]} | `{body[i][0][:80]}` |\n")
 
 
 if __name__ == "__main__":
