@@ -11,6 +11,8 @@ A step = one pass of the hot path over one batch of synthetic queries.
   value        device-resident inputs/outputs, CUDA events on the launching stream, max over ranks
   e2e          the public API with HOST (pinned) NumPy buffers: H2D + kernel + D2H inside the timing;
                e2e.ceiling = the same bytes moved by bare concurrent cudaMemcpyAsync (no kernel)
+  gather       (N > 1) the same step followed by an all-gather of the result shards over NCCL --
+               off the data path, reported separately
   roofline     of the dominant kernel: FP64 pipe (peak measured live with a DFMA probe) or HBM
   cpu_baseline the UNMODIFIED reference (oracle/_ref/site, pychebyshev 0.21.1) on this box's host
                cores, on a bounded sample of the same workload (rank 0, N=1)
@@ -756,8 +758,10 @@ def roofline_of(case, n_local, step_ms, peak_fp64, peaks, peak_note):
 
 def copy_ceiling(dev, h_in, h_out, d_in, d_out, reps=3, barrier=None):
     """The same host buffers moved by bare cudaMemcpyAsync, H2D and D2H concurrently on two
-    streams, no kernel: the end-to-end ceiling of this box for these byte counts.  Best of three
-    issue schemes (whole buffers, 64 MB and 256 MB chunks)."""
+    streams, no kernel: the end-to-end ceiling of this box for these byte counts.  Each scheme
+    (whole buffers, 64 MB and 256 MB chunks) is timed like the end-to-end region itself -- one
+    barrier, then `reps` rounds back to back, ranks free to drift apart -- and the best scheme
+    wins.  Returns seconds per round."""
     import torch
 
     s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -767,20 +771,21 @@ def copy_ceiling(dev, h_in, h_out, d_in, d_out, reps=3, barrier=None):
     for chunk_mb in (0, 64, 256):
         ci = t_in.numel() if not chunk_mb else (chunk_mb << 20) // 8
         co = t_out.numel() if not chunk_mb else max(1, ci * t_out.numel() // max(1, t_in.numel()))
-        for _ in range(reps):
+        for timed in (False, True):          # one untimed round per scheme, then the timed ones
             if barrier:
                 barrier()
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            with torch.cuda.stream(s1):
-                for o in range(0, t_in.numel(), ci):
-                    f_in[o:o + ci].copy_(t_in[o:o + ci], non_blocking=True)
-            with torch.cuda.stream(s2):
-                for o in range(0, t_out.numel(), co):
-                    t_out[o:o + co].copy_(f_out[o:o + co], non_blocking=True)
+            for _ in range(reps if timed else 1):
+                with torch.cuda.stream(s1):
+                    for o in range(0, t_in.numel(), ci):
+                        f_in[o:o + ci].copy_(t_in[o:o + ci], non_blocking=True)
+                with torch.cuda.stream(s2):
+                    for o in range(0, t_out.numel(), co):
+                        t_out[o:o + co].copy_(f_out[o:o + co], non_blocking=True)
             torch.cuda.synchronize(dev)
-            dt = time.perf_counter() - t0
-            if dt < best:
+            dt = (time.perf_counter() - t0) / max(1, reps)
+            if timed and dt < best:
                 best, how = dt, ("whole buffers" if not chunk_mb else f"{chunk_mb} MB chunks")
     return best, how
 
@@ -867,11 +872,89 @@ def run_ours(args, rank, local_rank, world):
                            "gbs_per_gpu": bytes_step / ceil_s / 1e9,
                            "gbs_total": world * bytes_step / ceil_s / 1e9,
                            "how": "same pinned buffers, H2D and D2H cudaMemcpyAsync concurrently on "
-                                  "two streams, no kernel, all ranks at once, best of 3 schemes x 3 "
-                                  f"repeats (this rank's best: {ceil_how})"},
+                                  "two streams, no kernel, all ranks at once; per scheme one "
+                                  "barrier then 3 rounds back to back (like the timed loop), best "
+                                  f"of 3 schemes (this rank's best: {ceil_how})"},
                "frac_of_ceiling": (e2e_total * args.steps / e2e_s) / (e2e_total / ceil_s),
                "host_pipeline": _engine.host_pipeline_info(local_rank)}
         del h_pts, h_out
+
+    # ---- optional result gather: off the data path, reported separately --------
+    gather = None
+    if world > 1 and case.scaling == "weak" and len(t.passes) == 1 and not getattr(case, "lookup", False):
+        from pychebyshev_b200 import sharding
+
+        g_steps = max(1, min(args.steps, 5))
+        recv = (world - 1) * t.block * G * 8
+        # (1) the library recipe: kernel, then NCCL all-gather, serialised
+        full = torch.empty((world * t.block, G), dtype=t.out.dtype, device=dev)
+        dist.all_gather_into_tensor(full, t.out)          # channel set-up, untimed
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        barrier()
+        ev[0].record()
+        for _ in range(g_steps):
+            dist.all_gather_into_tensor(full, t.out)
+        ev[1].record()
+        for _ in range(g_steps):
+            t.step()
+            dist.all_gather_into_tensor(full, t.out)
+        ev[2].record()
+        barrier()
+        alone_ms, both_ms = max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])])
+        nccl_full = full[rank * t.block: rank * t.block + 4096].clone()
+        del full
+        torch.cuda.empty_cache()
+        gather = {"unit": UNIT, "steps": g_steps, "bytes_received_per_rank_per_step": recv,
+                  "nccl": {"value": t.n_total * g_steps / (both_ms * 1e-3),
+                           "what": "kernel, then all_gather_into_tensor (NCCL) of every rank's (n x G) "
+                                   "shard into one replicated tensor, serialised",
+                           "gather_ms": alone_ms / g_steps,
+                           "gather_gbs_per_rank": recv / (alone_ms / g_steps * 1e-3) / 1e9}}
+        # (2) ours: the kernel writes its slice of a replicated tensor, the copy engines push each
+        #     chunk to the peers over NVLink underneath the next chunk's kernel (csrc/pcb_peer.cu)
+        try:
+            chunks = 8
+            pg = sharding.PeerGather(t.block, G, local_rank)
+            cut = [t.block * c // chunks for c in range(chunks + 1)]
+
+            def peer_step():
+                pg.join()                                  # last step's pushes read these rows
+                for a, b in zip(cut, cut[1:]):
+                    case.launch(t.plan, t.pts[a:b], pg.local[a:b])
+                    pg.push(a, b)
+
+            peer_step()
+            pg.publish()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(g_steps):
+                peer_step()
+            pg.join()
+            e1.record()
+            barrier()
+            (peer_ms,) = max_over_ranks([e0.elapsed_time(e1)])
+            got = pg.publish()
+            same = True
+            for r in range(world):                         # every replica holds every rank's rows
+                probe = got[r, :: max(1, t.block // 1000)].double().sum().reshape(1)
+                allp = [torch.empty_like(probe) for _ in range(world)]
+                dist.all_gather(allp, probe)
+                same = same and all(bool(torch.equal(allp[0], x)) for x in allp)
+            same = same and bool(torch.equal(got[rank, :4096], nccl_full))
+            gather["peer"] = {"value": t.n_total * g_steps / (peer_ms * 1e-3), "chunks": chunks,
+                              "what": "the kernel writes its slice of a replicated (world, n, G) tensor; "
+                                      "copy engines push each chunk into every peer's tensor over NVLink "
+                                      "(CUDA IPC mappings, one stream per peer) under the next chunk's "
+                                      "kernel; no NCCL on this path",
+                              "of_device_resident_value": (t.n_total * g_steps / (peer_ms * 1e-3)) / value,
+                              "egress_gbs_per_rank": recv * g_steps / (peer_ms * 1e-3) / 1e9,
+                              "replicas_agree": same}
+            pg.close()
+            del pg
+        except Exception as exc:  # noqa: BLE001  (IPC unavailable on this box: NCCL figure stands)
+            gather["peer"] = {"unavailable": repr(exc)}
+        gather["value"] = max(gather["nccl"]["value"], gather.get("peer", {}).get("value", 0.0))
 
     # ---- the other configs, each its own clocked measurement ------------------------------------
     del t.pts, t.out
@@ -937,6 +1020,8 @@ def run_ours(args, rank, local_rank, world):
         "config": cfg, "e2e": e2e, "gpu_launches": int(t.launches), "clocks": t.clocks,
         "roofline": roof, "checksum": checksum,
     }
+    if gather:
+        line["gather"] = gather
     if world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = reference_rate(case, seconds=args.cpu_seconds)

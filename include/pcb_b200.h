@@ -226,6 +226,31 @@ PCB_API int pcb_file_rewrite(const char *in_path, const char *out_path);
  * native loader derives for one dimension (reporting / tests). */
 PCB_API int pcb_file_grid_arrays(double lo, double hi, int n, double *nodes, double *weights, double *dmat);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optional result gather for query-sharded evaluation (reference: none -- the
+ * reference is single-process, its batch methods return one (N,) array, barycentric.py:992-1047).
+ * One process per GPU.  Each rank owns a replicated result tensor (world x rows x G doubles),
+ * exported as a CUDA IPC handle; the evaluators write this rank's slice of its own replica and
+ * pcb_peer_push copies that slice into every peer's replica with the copy engines over NVLink
+ * (one internal stream per peer), ordered after everything already enqueued on `stream`; `stream`
+ * itself does not wait, so the next chunk's kernel overlaps the copies.  pcb_peer_join makes
+ * `stream` wait for every push issued so far on that device (call it before the source slice is
+ * overwritten, and before the cross-process barrier that publishes the replicas).  No NCCL, no kernel.
+ *   pcb_peer_alloc : cudaMalloc + cudaIpcGetMemHandle (handle: PCB_PEER_HANDLE_BYTES bytes to send
+ *                    to the other processes by any host-side means)
+ *   pcb_peer_open  : map a peer's allocation into this process (enables peer access lazily)
+ *   pcb_peer_push  : d_src[0:bytes] -> peer_ptrs[i] + offset_bytes for i < n_peers (<= 16)
+ *   pcb_peer_join  : `stream` waits for all outstanding pushes of device `dev`
+ * ------------------------------------------------------------------------------------------ */
+#define PCB_PEER_HANDLE_BYTES 64
+PCB_API int pcb_peer_alloc(int dev, uint64_t bytes, void **d_ptr, unsigned char *handle);
+PCB_API int pcb_peer_free(int dev, void *d_ptr);
+PCB_API int pcb_peer_open(int dev, const unsigned char *handle, void **d_ptr);
+PCB_API int pcb_peer_close(int dev, void *d_ptr);
+PCB_API int pcb_peer_push(int dev, int n_peers, void *const *peer_ptrs, uint64_t offset_bytes,
+                          const void *d_src, uint64_t bytes, void *stream);
+PCB_API int pcb_peer_join(int dev, void *stream);
+
 /* Values of any plan kind (the plan's own number of outputs per point). */
 PCB_API int pcb_plan_eval(void *plan, const double *d_points, int64_t N, double *d_out, void *stream);
 

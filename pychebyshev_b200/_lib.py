@@ -69,6 +69,13 @@ SIGNATURES = {
     "pcb_plan_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pcb_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "pcb_launch_count": (C.c_int64, []),
+    "pcb_peer_alloc": (C.c_int, [C.c_int, C.c_uint64, _vpp, C.c_char_p]),
+    "pcb_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "pcb_peer_open": (C.c_int, [C.c_int, C.c_char_p, _vpp]),
+    "pcb_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "pcb_peer_push": (C.c_int, [C.c_int, C.c_int, _vpp, C.c_uint64, C.c_void_p, C.c_uint64,
+                                C.c_void_p]),
+    "pcb_peer_join": (C.c_int, [C.c_int, C.c_void_p]),
 }
 
 _lib = None
