@@ -913,9 +913,12 @@ def run_ours(args, rank, local_rank, world):
         # (2) ours: the kernel writes its slice of a replicated tensor, the copy engines push each
         #     chunk to the peers over NVLink underneath the next chunk's kernel (csrc/pcb_peer.cu)
         try:
-            chunks = 8
+            # quarter-size chunks, then halving ones: the only push nothing hides is the last
+            # chunk's, so it is the smallest (1/32 of the shard)
+            frac = [0.0, 0.25, 0.5, 0.75, 0.875, 0.9375, 0.96875, 1.0]
+            chunks = len(frac) - 1
             pg = sharding.PeerGather(t.block, G, local_rank)
-            cut = [t.block * c // chunks for c in range(chunks + 1)]
+            cut = [int(t.block * f) for f in frac]
 
             def peer_step():
                 pg.join()                                  # last step's pushes read these rows

@@ -277,3 +277,42 @@ def test_slider_random_partitions(case):
     for g, o in enumerate(orders):
         G.assert_close_scaled(got[:, g], ref[:, g], 1.0, f"slider D={D} partition={partition} order {o}",
                               rel=2e-11 if any(o) else G.REL)
+
+
+# ------------------------------------------------------------------------------------------
+# .pcb files written by the reference, read by the native loader (no Python on the path)
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", range(8))
+def test_pcb_files_written_by_the_reference(case, tmp_path):
+    _ref()
+    import pychebyshev_b200 as pcb
+    from oracle import ref_objects as RO
+
+    rng = np.random.default_rng(BASE_SEED + 5000 + case)
+    D = 1 + case % 4
+    domain = _domain(rng, D)
+    path = tmp_path / "f.pcb"
+    if case % 2 == 0:
+        n_nodes = _full_shape(rng, D, 60_000)
+        obj = RO.full_from_func(_smooth(rng, domain), domain, n_nodes)
+        pts = _queries(rng, domain, 600, nodes=obj.nodes)
+        kind = "approx"
+    else:
+        n_nodes = [int(v) for v in rng.integers(3, 12, D)]
+        knots = [sorted(float(v) for v in rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo),
+                                                      int(rng.integers(0, 3))))
+                 for lo, hi in domain]
+        obj = RO.spline_from_func(_smooth(rng, domain), domain, n_nodes, knots)
+        pts = _queries(rng, domain, 600, knots=knots)
+        kind = "spline"
+    obj.save(str(path), format="binary")
+    orders = _order_rows(rng, D, 4)
+    plan = pcb.load_plan(path, orders=orders)
+    assert plan.kind == kind and plan.G == len(orders)
+    got = plan.eval(pts)
+    for g, o in enumerate(orders):
+        ref = obj.vectorized_eval_batch(pts, list(o)) if kind == "approx" else obj.eval_batch(pts, o)
+        # the loader rebuilds nodes, weights and differentiation matrices natively from the header
+        # (no arrays of the reference object are shared): same 1e-12-class bound
+        G.assert_close_scaled(got[:, g], ref, 1.0, f".pcb {kind} D={D} n={n_nodes} order {o}")
