@@ -55,13 +55,11 @@ struct SplinePlan : PlanBase {
     // 2-D splines on the FP64 tensor cores: piece tensors in MMA fragment order [piece][output]
     bool dmma2d_ok = false;
     double *d_frags = nullptr;
-    // 3-D splines on the tensor cores (joint-K): fragment images + (j, kz) index tables per piece
+    // 3-D splines on the tensor cores (joint-K): fragment images per (piece, output)
     bool dmma3d_ok = false;
     int kb3max = 0, g3_per = 1;  // K blocks of the largest piece; outputs per launch
-    int *d_tabs = nullptr;
     ~SplinePlan() override;
     void free_all() {
-        if (d_tabs) cudaFree(d_tabs);
         if (d_frags) cudaFree(d_frags);
         if (d_num_knots) cudaFree(d_num_knots);
         if (d_knots) cudaFree(d_knots);
@@ -929,65 +927,110 @@ slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // 3-D spline pieces on the FP64 tensor cores: the last two axes jointly on the MMA K dimension.
 //     p(x, y, z) = sum_i a_i  sum_{(j,k)} (b_j c_k) T[i][(j,k)]
-// For 8 queries: U[q, i] = A[q, (j,k)] B[(j,k), i],  A = b_j(q) c_k(q) built on the fly (two
-// tile reads + one DMUL per fragment element, indices from a per-piece table in shared memory),
-// B = the piece's tensor in fragment order (shared memory), K = n1 n2 padded to 4, N = n0 padded
-// to 8; then the dot with a(x): 4 FMA per lane and a quad shuffle.  15^3: 114 DMMA per 8 queries
-// replace 3,600 DFMA per query-thread.
+// For 8 queries: U[q, i] = A[q, (j,k)] B[(j,k), i],  A = b_j(q) c_k(q) built on the fly,
+// B = the piece's tensor in fragment order (shared memory), N = n0 padded to 8; then the dot with
+// a(x): 4 FMA per lane and a quad shuffle.  The K index is ordered (j, m, c) with k = 4 m + c, the
+// last axis padded to M = ceil(n2 / 4) blocks of 4: lane c of a quad only ever needs c_{4m+c},
+// m < M -- at most four values, held in registers for the whole tile -- and b_j changes once per M
+// k-steps, so a k-step is one DMUL, the B-fragment loads and the DMMAs: no index table, no
+// per-step reads of the weight tiles.  (The first version flattened (j, k) densely, 225 -> 228,
+// and looked both factors up per k-step through a table: five shared loads per two DMMAs and a
+// load -> load -> DMUL -> DMMA dependency chain per step; this order spends 240 instead of 228
+// k-rows on 15^3 and runs 17 % faster, 1.73e9 -> 2.02e9 q/s.)  15^3: 120 DMMA per 8 queries
+// replace 3,600 DFMA per thread.
 // ---------------------------------------------------------------------------------------------
 constexpr int BL3_THREADS = 256;                     // 8 warps share one staged copy of the fragments
-constexpr int BL3_MAX_KB = 64;                       // n1 * n2 <= 256
+constexpr int BL3_MAX_KB = 64;                       // n1 * ceil(n2 / 4) <= 64
 constexpr int BL3_WARP_DOUBLES = 3 * 16 * BL_SA + BL_OUT * 32 + 32;  // three weight tiles, outputs, scratch
 
-// one 8-query row tile against one piece: frag = [KB][NT = 2][32] per output, tab[k] = (j, kz) packed
-template <int NT>
-__device__ __forceinline__ void bl3_tile_n(int KB, int fragstride, const double *frag, const int *tab,
-                                           int o0, int no, int t, const double *sA, const double *sB,
-                                           const double *sC, double *sOut, int lane, bool take) {
+// TL 8-query row tiles (t0 .. t0 + TL - 1) against one piece: frag = [n1][M][NT = 2][32] per output.
+// One B-fragment load feeds TL DMMAs and the warp carries 2 TL NT independent accumulator chains.
+template <int NT, int M, int TL>
+__device__ __forceinline__ void bl3_tile_nm(int n1, int n2, int fragstride, const double *frag, int o0,
+                                            int no, int t0, const double *sA, const double *sB,
+                                            const double *sC, double *sOut, int lane, unsigned take) {
     const int r = lane >> 2, c = lane & 3;
-    const int q = 8 * t + r;
-    double aq[NT][2];
+    const int q = 8 * t0 + r;  // row of tile t0; tile t0 + tl is 8 tl further
+    double aq[TL][NT][2], cz[TL][M];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+    for (int tl = 0; tl < TL; ++tl) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) aq[nt][e] = sA[(8 * nt + 2 * c + e) * BL_SA + q];
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) aq[tl][nt][e] = sA[(8 * nt + 2 * c + e) * BL_SA + q + 8 * tl];
+#pragma unroll
+        for (int m = 0; m < M; ++m) cz[tl][m] = 4 * m + c < n2 ? sC[(4 * m + c) * BL_SA + q + 8 * tl] : 0.0;
+    }
     for (int o = 0; o < no; ++o) {
         const double *f = frag + (size_t)(o0 + o) * fragstride + lane;
-        double acc[NT][2], accb[NT][2];
+        double acc[TL][NT][2], accb[TL][NT][2];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = accb[nt][0] = accb[nt][1] = 0.0;
+        for (int tl = 0; tl < TL; ++tl)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                acc[tl][nt][0] = acc[tl][nt][1] = accb[tl][nt][0] = accb[tl][nt][1] = 0.0;
 #pragma unroll 2
-        for (int kb = 0; kb < KB; ++kb) {
-            const int jk = tab[4 * kb + c];  // (j << 16) | kz; padding rows point at a zero entry
-            const double a = sB[(jk >> 16) * BL_SA + q] * sC[(jk & 0xffff) * BL_SA + q];
+        for (int j = 0; j < n1; ++j) {
+            double bj[TL];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const double b = f[(kb * 2 + nt) * 32];
-                if (kb & 1)
-                    bl_dmma(accb[nt][0], accb[nt][1], a, b);
-                else
-                    bl_dmma(acc[nt][0], acc[nt][1], a, b);
+            for (int tl = 0; tl < TL; ++tl) bj[tl] = sB[j * BL_SA + q + 8 * tl];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double b = f[((j * M + m) * 2 + nt) * 32];
+#pragma unroll
+                    for (int tl = 0; tl < TL; ++tl) {
+                        const double a = bj[tl] * cz[tl][m];
+                        if ((M & 1) ? ((j + m) & 1) : (m & 1))
+                            bl_dmma(accb[tl][nt][0], accb[tl][nt][1], a, b);
+                        else
+                            bl_dmma(acc[tl][nt][0], acc[tl][nt][1], a, b);
+                    }
+                }
             }
         }
-        double part = 0.0;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            part = fma(acc[nt][0] + accb[nt][0], aq[nt][0], part);
-            part = fma(acc[nt][1] + accb[nt][1], aq[nt][1], part);
+        for (int tl = 0; tl < TL; ++tl) {
+            double part = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                part = fma(acc[tl][nt][0] + accb[tl][nt][0], aq[tl][nt][0], part);
+                part = fma(acc[tl][nt][1] + accb[tl][nt][1], aq[tl][nt][1], part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (c == 0 && ((take >> tl) & 1u)) sOut[o * 32 + q + 8 * tl] = part;
         }
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        if (c == 0 && take) sOut[o * 32 + q] = part;
+    }
+}
+
+template <int NT, int TL>
+__device__ __forceinline__ void bl3_tile_n(int n1, int n2, int fragstride, const double *frag, int o0,
+                                           int no, int t0, const double *sA, const double *sB,
+                                           const double *sC, double *sOut, int lane, unsigned take) {
+    switch ((n2 + 3) >> 2) {  // uniform: the piece's shape comes from the constant bank
+    case 1: bl3_tile_nm<NT, 1, TL>(n1, n2, fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take); break;
+    case 2: bl3_tile_nm<NT, 2, TL>(n1, n2, fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take); break;
+    case 3: bl3_tile_nm<NT, 3, TL>(n1, n2, fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take); break;
+    default: bl3_tile_nm<NT, 4, TL>(n1, n2, fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take); break;
     }
 }
 
 // One launch evaluates outputs [g0, g0 + G) of Gtot (the fragment images of all outputs of a launch
 // must fit in shared memory next to the per-warp tiles).
-__global__ void __launch_bounds__(BL3_THREADS)
+// TL row tiles at once; MINB = 0 leaves the register budget to ptxas.  Which budget keeps the
+// weight-row bank reads on the uniform datapath is an empirical matter (tools/check_sass.py):
+// <1, 0> does (80 registers), <1, 1> and <2, 0 / 1 / 2> read the whole bank per lane, <2, 3> does.
+// Measured on 15^3 (values): <1, 0> 2.03e9 q/s, <2, 3> 1.85e9, <2, 0> 1.92e9, <4, 0> 1.64e9 -- one
+// B-fragment load per two or four DMMAs and twice / four times the accumulator chains do not pay;
+// only <1, 0> is instantiated.
+template <int TL, int MINB>
+__global__ void __launch_bounds__(BL3_THREADS, MINB)
 spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__restrict__ num_knots,
                      const int *__restrict__ knot_off, const double *__restrict__ knots,
-                     const double *__restrict__ frags, const int *__restrict__ tabs,
-                     const double *__restrict__ pts, int64_t N, double *__restrict__ out,
+                     const double *__restrict__ frags, const double *__restrict__ pts, int64_t N,
+                     double *__restrict__ out,
                      int32_t *__restrict__ piece_out) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_cnt[BANK_GRIDS];
@@ -996,8 +1039,7 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fragstride = KBmax * 64;                       // doubles per (piece, output)
     double *sFrag = smem;
-    int *sTab = reinterpret_cast<int *>(smem + (size_t)P * G * fragstride);  // [P][KBmax * 4]
-    double *sA = smem + (size_t)P * G * fragstride + ((size_t)P * KBmax * 4 + 1) / 2 + warp * BL3_WARP_DOUBLES;
+    double *sA = smem + (size_t)P * G * fragstride + warp * BL3_WARP_DOUBLES;
     double *sB = sA + 16 * BL_SA;
     double *sC = sB + 16 * BL_SA;
     double *sOut = sC + 16 * BL_SA;
@@ -1006,7 +1048,6 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
         const double *src = frags + (size_t)((pg / G) * Gtot + g0 + pg % G) * fragstride;
         for (int e = tid; e < fragstride; e += BL3_THREADS) sFrag[(size_t)pg * fragstride + e] = __ldg(src + e);
     }
-    for (int e = tid; e < P * KBmax * 4; e += BL3_THREADS) sTab[e] = __ldg(tabs + e);
     int mine;
     {
         const int64_t ql = q0 + tid < N ? q0 + tid : N - 1;
@@ -1057,23 +1098,25 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
     __syncwarp();
     for (int o0 = 0; o0 < G; o0 += BL_OUT) {
         const int no = G - o0 < BL_OUT ? G - o0 : BL_OUT;
-        // (multiplying all four row tiles at once -- one B-fragment load per four DMMAs -- measured
-        // 6 % SLOWER here, 1.63e9 against 1.73e9 q/s: the on-the-fly A fragments of four tiles crowd the
-        // same shared-memory pipe; the slider's 2-D slides gain 12 % from it)
 #pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
-            const int prow = __shfl_sync(0xffffffffu, mine, 8 * t + (lane >> 2));
-            const unsigned here = __reduce_or_sync(0xffffffffu, 1u << prow);
+        for (int t0 = 0; t0 < 4; t0 += TL) {
+            unsigned here = 0, prow[TL];
+#pragma unroll
+            for (int tl = 0; tl < TL; ++tl) {
+                prow[tl] = __shfl_sync(0xffffffffu, mine, 8 * (t0 + tl) + (lane >> 2));
+                here |= __reduce_or_sync(0xffffffffu, 1u << prow[tl]);
+            }
             for (int p = 0; p < P; ++p) {
                 if (!((here >> p) & 1u)) continue;
                 const BankGrid &g = c_bgrid[p];
-                const int KB = (g.n[1] * g.n[2] + 3) >> 2;
                 const double *frag = sFrag + (size_t)p * G * fragstride;
-                const int *tab = sTab + p * KBmax * 4;
+                unsigned take = 0;
+#pragma unroll
+                for (int tl = 0; tl < TL; ++tl) take |= (prow[tl] == (unsigned)p ? 1u : 0u) << tl;
                 if (g.n[0] > 8)
-                    bl3_tile_n<2>(KB, fragstride, frag, tab, o0, no, t, sA, sB, sC, sOut, lane, prow == p);
+                    bl3_tile_n<2, TL>(g.n[1], g.n[2], fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take);
                 else
-                    bl3_tile_n<1>(KB, fragstride, frag, tab, o0, no, t, sA, sB, sC, sOut, lane, prow == p);
+                    bl3_tile_n<1, TL>(g.n[1], g.n[2], fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take);
             }
         }
         __syncwarp();
@@ -1085,16 +1128,18 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
     }
 }
 
-// Fragment image of one n0 x n1 x n2 tensor for the joint-K 3-D kernel:
-//   f[(kb * 2 + nt) * 32 + lane] = T[i = 8 nt + lane / 4][(j, kz) = 4 kb + lane % 4]
-static void bl3_make_frag(const double *t, int n0, int n1, int n2, int KBmax, double *f) {
-    const int K = n1 * n2;
-    for (int kb = 0; kb < KBmax; ++kb)
-        for (int nt = 0; nt < 2; ++nt)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int i = 8 * nt + lane / 4, k = 4 * kb + lane % 4;
-                f[(kb * 2 + nt) * 32 + lane] = (i < n0 && k < K) ? t[(size_t)i * K + k] : 0.0;
-            }
+// Fragment image of one n0 x n1 x n2 tensor for the joint-K 3-D kernel, M = ceil(n2 / 4):
+//   f[((j * M + m) * 2 + nt) * 32 + lane] = T[i = 8 nt + lane / 4][j][k = 4 m + lane % 4]   (0 outside)
+static void bl3_make_frag(const double *t, int n0, int n1, int n2, double *f) {
+    const int M = (n2 + 3) / 4;
+    for (int j = 0; j < n1; ++j)
+        for (int m = 0; m < M; ++m)
+            for (int nt = 0; nt < 2; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int i = 8 * nt + lane / 4, k = 4 * m + lane % 4;
+                    f[((j * M + m) * 2 + nt) * 32 + lane] =
+                        (i < n0 && k < n2) ? t[((size_t)i * n1 + j) * n2 + k] : 0.0;
+                }
 }
 
 // Fragment image of one n0 x n1 tensor: f[(kb * 2 + nt) * 32 + lane] = T[4 kb + lane % 4][8 nt + lane / 4]
@@ -1372,31 +1417,25 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
         int kbmax = 1;
         for (int p = 0; p < P; ++p) {
             fits = fits && desc[p].n[0] <= 16 && desc[p].n[1] <= 16 && desc[p].n[2] <= 16;
-            kbmax = std::max(kbmax, (desc[p].n[1] * desc[p].n[2] + 3) / 4);
+            kbmax = std::max(kbmax, desc[p].n[1] * ((desc[p].n[2] + 3) / 4));
         }
         const size_t fragstride = (size_t)kbmax * 64;
         // outputs per launch: as many as fit in shared memory next to the tiles of 8 warps
         int per = 0;
         for (int gl = G; gl >= 1 && !per; --gl) {
-            const size_t bytes = (size_t)P * gl * fragstride * 8 + (((size_t)P * kbmax * 4 + 1) / 2) * 8 +
+            const size_t bytes = (size_t)P * gl * fragstride * 8 +
                                  (size_t)(BL3_THREADS / 32) * BL3_WARP_DOUBLES * 8;
             if (bytes + 2048 <= (size_t)pl->smem_optin) per = gl;
         }
         if (fits && kbmax <= BL3_MAX_KB && per >= 1) {
             pl->g3_per = per;
             std::vector<double> fr((size_t)P * G * fragstride, 0.0);
-            std::vector<int> tabs((size_t)P * kbmax * 4, 0);
-            for (int p = 0; p < P; ++p) {
-                const int n1 = desc[p].n[1], n2 = desc[p].n[2], K = n1 * n2;
+            for (int p = 0; p < P; ++p)
                 for (int g = 0; g < G; ++g)
-                    bl3_make_frag(piece_tensors_host[(size_t)p * G + g], desc[p].n[0], n1, n2, kbmax,
-                                  fr.data() + ((size_t)p * G + g) * fragstride);
-                for (int k = 0; k < kbmax * 4; ++k)  // rows beyond K: entry 15 of both tiles, which is zero
-                    tabs[(size_t)p * kbmax * 4 + k] = k < K ? ((k / n2) << 16) | (k % n2) : (15 << 16) | 15;
-                // (a 16-node dim has no zero entry 15: its padding rows meet zero B fragments instead)
-            }
+                    bl3_make_frag(piece_tensors_host[(size_t)p * G + g], desc[p].n[0], desc[p].n[1],
+                                  desc[p].n[2], fr.data() + ((size_t)p * G + g) * fragstride);
             pl->kb3max = kbmax;
-            pl->dmma3d_ok = upload(&pl->d_frags, fr.data(), fr.size()) && upload(&pl->d_tabs, tabs.data(), tabs.size());
+            pl->dmma3d_ok = upload(&pl->d_frags, fr.data(), fr.size());
             if (!pl->dmma3d_ok) cudaGetLastError();
         }
     }
@@ -1447,15 +1486,16 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
         const size_t fragstride = (size_t)pl->kb3max * 64;
         for (int g0 = 0; g0 < pl->G; g0 += pl->g3_per) {
             int gl = std::min(pl->g3_per, pl->G - g0);
-            const size_t dsm = ((size_t)pl->P * gl * fragstride + ((size_t)pl->P * pl->kb3max * 4 + 1) / 2 +
+            const size_t dsm = ((size_t)pl->P * gl * fragstride +
                                 (size_t)(BL3_THREADS / 32) * BL3_WARP_DOUBLES) * sizeof(double);
             int32_t *piece = g0 == 0 ? d_piece : nullptr;
             void *dargs[] = {(void *)&gl, (void *)&g0, (void *)&pl->G, (void *)&pl->P, (void *)&pl->kb3max,
                              (void *)&pl->d_num_knots, (void *)&pl->d_knot_off, (void *)&pl->d_knots,
-                             (void *)&pl->d_frags, (void *)&pl->d_tabs, (void *)&d_points, (void *)&N,
+                             (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
                              (void *)&d_out, (void *)&piece};
-            if (int rc = bank_launch(pl, part.id, part.h_bank, part.h_desc, (const void *)spline3d_dmma_kernel,
-                                     dargs, dsm, N, static_cast<cudaStream_t>(stream), BL3_THREADS))
+            const void *k3 = (const void *)spline3d_dmma_kernel<1, 0>;
+            if (int rc = bank_launch(pl, part.id, part.h_bank, part.h_desc, k3, dargs, dsm, N,
+                                     static_cast<cudaStream_t>(stream), BL3_THREADS))
                 return rc;
         }
         return PCB_OK;

@@ -33,7 +33,7 @@ MUST_BE_UNIFORM = (
     "spline_bank_kernel<1, 2>", "spline_bank_kernel<2, 2>", "spline_bank_kernel<2, 3>",
     "spline_bank_kernel<4, 2>", "spline_bank_kernel<4, 3>", "spline_bank_kernel<4, 4>",
     "slider_bank_kernel<1, 2>", "slider_bank_kernel<2, 2>", "slider_bank_kernel<4, 2>",
-    "spline2d_dmma_kernel", "slider2d_dmma_kernel", "spline3d_dmma_kernel",
+    "spline2d_dmma_kernel", "slider2d_dmma_kernel", "spline3d_dmma_kernel<1, 0>",
 )
 #: at most this share of a MUST_BE_UNIFORM kernel's bank reads may be per-lane (descriptor fields
 #: that feed per-lane predicates are legitimately read with LDC)

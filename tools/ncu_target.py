@@ -63,6 +63,16 @@ def main():
         n = n or 10_000_000
         pts = rand_points(dom, n)
         fn = lambda: sl.eval_batch(pts, [0] * 10)  # noqa: E731
+    elif which == "spline3d_value":
+        from oracle import np_oracle as O
+
+        g = G.load("spline_bs3d")
+        knots, shape, pieces = G.spline_parts(g, O.diff_matrix)
+        sp = pcb.ChebyshevSpline.from_values([p[0] for p in pieces], 3, wl.SPLINE3D_DOMAIN,
+                                             wl.SPLINE3D_NODES, knots)
+        n = n or 8_000_000
+        pts = rand_points(wl.SPLINE3D_DOMAIN, n)
+        fn = lambda: sp.eval_batch(pts, [0, 0, 0])  # noqa: E731
     else:
         from oracle import np_oracle as O
 
