@@ -1033,7 +1033,7 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
                      const int *__restrict__ knot_off, const double *__restrict__ knots,
                      const double *__restrict__ frags, const double *__restrict__ pts, int64_t N,
                      double *__restrict__ out,
-                     int32_t *__restrict__ piece_out) {
+                     int32_t *__restrict__ piece_out, int qper) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_cnt[BANK_GRIDS];
     __shared__ unsigned short s_perm[BL3_THREADS];
@@ -1045,8 +1045,12 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
     double *sB = sA + 16 * BL3_SA;
     double *sC = sB + 16 * BL3_SA;
     double *sOut = sC + 16 * BL3_SA;
-    const int nthr = blockDim.x;                              // 256 or 384, the launcher's choice
-    const int64_t q0 = (int64_t)blockIdx.x * nthr;
+    // The CTA takes qper <= blockDim.x queries.  With few pieces the launcher leaves 8 (P - 1) slots
+    // free so that every piece's run of sorted queries can start on an 8-query tile boundary: no
+    // row tile then mixes pieces, none is contracted twice, and all warps finish together (a CTA
+    // waits for its slowest warp; with 2 pieces one warp would run 5 tile passes against 4).
+    const int64_t q0 = (int64_t)blockIdx.x * qper;
+    const bool aligned = qper < (int)blockDim.x;
     // The fragment images (image of (piece p, output g0 + o) -> slot p * G + o) arrive by TMA bulk
     // copies behind an mbarrier while the CTA routes, sorts and builds its weight rows; the first
     // reader is the contraction.
@@ -1060,27 +1064,38 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
                      frags + (size_t)((pg / G) * Gtot + g0 + pg % G) * fragstride,
                      (uint32_t)(fragstride * sizeof(double)), &s_bar);
     }
+    const bool has = tid < qper;  // slots beyond qper carry no query of their own
     int mine;
     {
-        const int64_t ql = q0 + tid < N ? q0 + tid : N - 1;
+        const int64_t ql = has && q0 + tid < N ? q0 + tid : (q0 < N ? q0 : N - 1);
         mine = spline_piece_index(3, num_knots, knot_off, knots, pts + ql * 3);
-        if (piece_out && q0 + tid < N) piece_out[q0 + tid] = mine;
+        if (piece_out && has && q0 + tid < N) piece_out[q0 + tid] = mine;
     }
     if (tid < BANK_GRIDS) s_cnt[tid] = 0;
+    s_perm[tid] = 0xffffu;
     __syncthreads();
-    const unsigned peers = __match_any_sync(0xffffffffu, mine);
+    const unsigned peers = __match_any_sync(0xffffffffu, has ? mine : -1);
     const int leader = __ffs(peers) - 1;
     int warp_off = 0;
-    if (lane == leader) warp_off = atomicAdd(&s_cnt[mine], __popc(peers));
+    if (has && lane == leader) warp_off = atomicAdd(&s_cnt[mine], __popc(peers));
     warp_off = __shfl_sync(0xffffffffu, warp_off, leader);
     __syncthreads();
-    int pos = warp_off + __popc(peers & ((1u << lane) - 1u));
-    for (int p = 0; p < P; ++p) pos += p < mine ? s_cnt[p] : 0;
-    s_perm[pos] = (unsigned short)tid;
-    s_piece[pos] = (unsigned char)mine;
+    if (has) {
+        int pos = warp_off + __popc(peers & ((1u << lane) - 1u));
+        for (int p = 0; p < P; ++p) pos += p < mine ? (aligned ? (s_cnt[p] + 7) & ~7 : s_cnt[p]) : 0;
+        s_perm[pos] = (unsigned short)tid;
+        s_piece[pos] = (unsigned char)mine;
+    }
     __syncthreads();
-    mine = s_piece[tid];
-    const int64_t q = q0 + s_perm[tid];
+    int src = s_perm[tid];
+    if (src == 0xffff) {  // padding slot: evaluates the CTA's first query on its run's piece, stores nothing
+        int p = 0;
+        for (int end = (s_cnt[0] + 7) & ~7; tid >= end && p + 1 < P; end += (s_cnt[p] + 7) & ~7) ++p;
+        mine = p;
+    } else {
+        mine = s_piece[tid];
+    }
+    const int64_t q = src == 0xffff ? N : q0 + src;
     const bool live = q < N;
     const double *x = pts + (live ? q : N - 1) * 3;
     double *o = out + (live ? q : N - 1) * Gtot + g0;
@@ -1239,9 +1254,11 @@ static bool bank_build(const std::vector<GridDesc> &desc, const std::vector<doub
 
 static int bank_launch(const PlanBase *pl, uint64_t plan_id, const std::vector<double> &h_bank,
                        const std::vector<BankGrid> &h_desc, const void *kernel, void **args,
-                       size_t smem, int64_t N, cudaStream_t st, int threads = BANK_THREADS) {
+                       size_t smem, int64_t N, cudaStream_t st, int threads = BANK_THREADS,
+                       int per_cta = 0) {  // queries per CTA when not one per thread
     PCB_CUDA(allow_dynamic_smem(kernel, smem, pl->smem_optin));
-    const int64_t blocks = (N + threads - 1) / threads;
+    if (per_cta <= 0) per_cta = threads;
+    const int64_t blocks = (N + per_cta - 1) / per_cta;
     PCB_REQUIRE(blocks <= 0x7fffffffLL, "batch too large for one launch");
     const int rc = g_grid_bank.acquire(pl->dev, plan_id, st, [&](cudaStream_t s) {
         cudaError_t e = cudaMemcpyToSymbolAsync(c_grid, h_bank.data(), h_bank.size() * sizeof(double), 0,
@@ -1511,13 +1528,17 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
             const size_t dsm = ((size_t)pl->P * gl * fragstride +
                                 (size_t)pl->g3_warps * BL3_WARP_DOUBLES) * sizeof(double);
             int32_t *piece = g0 == 0 ? d_piece : nullptr;
+            // few pieces: 8 (P - 1) free slots per CTA let every piece's run start on a tile boundary
+            const int threads = 32 * pl->g3_warps;
+            const int slack = 8 * (pl->P - 1);
+            int qper = slack * 8 <= threads && !getenv("PCB_BL3_UNALIGNED") ? threads - slack : threads;
             void *dargs[] = {(void *)&gl, (void *)&g0, (void *)&pl->G, (void *)&pl->P, (void *)&pl->kb3max,
                              (void *)&pl->d_num_knots, (void *)&pl->d_knot_off, (void *)&pl->d_knots,
                              (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
-                             (void *)&d_out, (void *)&piece};
+                             (void *)&d_out, (void *)&piece, (void *)&qper};
             const void *k3 = (const void *)spline3d_dmma_kernel<1, 0>;
             if (int rc = bank_launch(pl, part.id, part.h_bank, part.h_desc, k3, dargs, dsm, N,
-                                     static_cast<cudaStream_t>(stream), 32 * pl->g3_warps))
+                                     static_cast<cudaStream_t>(stream), threads, qper))
                 return rc;
         }
         return PCB_OK;
