@@ -1,3 +1,5 @@
+# Full validation of a build on one B200: GPU test suite, smoke, both bench arms, one ncu capture,
+# the launch list of the bench command.   gpurun --timeout 1800 -- 'bash tools/gpu/validate.sh'
 set +e
 mkdir -p gpurun_out
 (time python -m pytest tests -q -m gpu -p no:cacheprovider) > gpurun_out/r2_gputests.log 2>&1
