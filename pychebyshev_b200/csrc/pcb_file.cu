@@ -64,7 +64,7 @@ static int parse_pcb(const char *path, PcbFile *out) {
     if (!take(raw, pos, out->lo.data(), 8 * D) || !take(raw, pos, out->hi.data(), 8 * D))
         return fail(PCB_EINVAL, "unexpected EOF reading f64 array");
     for (uint32_t d = 0; d < D; ++d)
-        if (!(out->lo[d] < out->hi[d]))
+        if (out->lo[d] >= out->hi[d])  // exactly the reference's test (_binary.py:262-266): NaN bounds pass
             return fail(PCB_EINVAL, "domain[%u]: lo (%g) must be < hi (%g)", d, out->lo[d], out->hi[d]);
     std::vector<uint32_t> nn(D);
     if (!take(raw, pos, nn.data(), 4 * D)) return fail(PCB_EINVAL, "unexpected EOF reading uint32 array");
@@ -120,6 +120,20 @@ static int parse_pcb(const char *path, PcbFile *out) {
     out->values.resize(per * (size_t)out->P);
     if (!take(raw, pos, out->values.data(), 8 * per * (size_t)out->P))
         return fail(PCB_EINVAL, "unexpected EOF reading f64 array");
+    // what the reference's reader goes on to check by constructing through from_values
+    // (spline.py:1272-1291, barycentric.py:1879-1880): knots strictly inside the domain, finite values
+    if (out->kind == 2) {
+        size_t off = 0;
+        for (uint32_t d = 0; d < D; ++d) {
+            for (uint32_t k = 0; k < (uint32_t)out->num_knots[d]; ++k) {
+                const double v = out->knots[off + k];
+                if (!(out->lo[d] < v && v < out->hi[d]))
+                    return fail(PCB_EINVAL, "Knot %g for dimension %u is not strictly inside domain [%g, %g]",
+                                v, d, out->lo[d], out->hi[d]);
+            }
+            off += (size_t)out->num_knots[d];
+        }
+    }
     for (double v : out->values)
         if (!std::isfinite(v)) return fail(PCB_EINVAL, "tensor_values contains NaN or Inf");
     return PCB_OK;
@@ -232,7 +246,7 @@ static int write_file(const char *path, const std::vector<unsigned char> &raw) {
 static int check_grid(int D, const double *lo, const double *hi, const int32_t *n) {
     PCB_REQUIRE(D >= 1 && D <= 64, "num_dimensions must be >= 1, got %d", D);
     for (int d = 0; d < D; ++d) {
-        PCB_REQUIRE(lo[d] < hi[d], "domain[%d]: lo (%g) must be < hi (%g)", d, lo[d], hi[d]);
+        PCB_REQUIRE(!(lo[d] >= hi[d]), "domain[%d]: lo (%g) must be < hi (%g)", d, lo[d], hi[d]);
         PCB_REQUIRE(n[d] >= 1, "n_nodes[%d] must be >= 1, got %d", d, n[d]);
     }
     return PCB_OK;
