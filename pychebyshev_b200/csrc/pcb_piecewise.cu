@@ -54,6 +54,7 @@ struct SplinePlan : PlanBase {
     size_t bank_smem = 0;
     // 2-D splines on the FP64 tensor cores: piece tensors in MMA fragment order [piece][output]
     bool dmma2d_ok = false;
+    int nfix = 0;  // node count shared by every dimension of every piece (0: mixed)
     double *d_frags = nullptr;
     // 3-D splines on the tensor cores (joint-K): fragment images per (piece, output)
     bool dmma3d_ok = false;
@@ -89,6 +90,7 @@ struct SliderPlan : PlanBase {
     double *d_frags = nullptr;
     int *d_frag_off = nullptr;
     int nfrag = 0;
+    int nfix = 0;  // node count shared by both dimensions of every slide (0: mixed)
     ~SliderPlan() override;
     void free_all() {
         if (d_frags) cudaFree(d_frags);
@@ -607,18 +609,40 @@ __device__ __forceinline__ void bl_dmma(double &c0, double &c1, double a, double
 // of the switch and storing it afterwards takes every bank read of the kernel off the uniform
 // datapath -- and so does a register cap (`__launch_bounds__(.., minBlocks)`), which is why these
 // kernels carry none (they need 72-78 registers).
-template <typename Coord>
+// Kernel variants for plans whose grids all have the same node count in every dimension.
+#define PCB_NFIX_KERNEL(nf, ...)                                                        \
+    ((nf) == 8    ? (const void *)__VA_ARGS__<8>                                        \
+     : (nf) == 11 ? (const void *)__VA_ARGS__<11>                                       \
+     : (nf) == 12 ? (const void *)__VA_ARGS__<12>                                       \
+     : (nf) == 15 ? (const void *)__VA_ARGS__<15>                                       \
+     : (nf) == 16 ? (const void *)__VA_ARGS__<16>                                       \
+                  : (const void *)__VA_ARGS__<0>)
+
+// NFIX > 0: every dimension of every grid of the plan has NFIX nodes, known at compile time -- the row
+// builder is then straight-line code; through the 16-way switch ptxas tail-merges the per-length
+// cases into one chain of blocks joined by uniform branches (~6 extra instructions per node).
+template <int NFIX, typename Coord>
 __device__ __forceinline__ double bl_rows(const BankGrid &g, Coord x, bool keep, double *sA, double *sB,
                                           int lane) {
     double row[GRID_NL];
     double *dump = sA + 16 * BL_SA + 16 * BL_SB + BL_OUT * 32;  // 32 doubles per warp
-    const double sa = bank_row<2>(x(0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
-                                  __double_as_longlong(c_grid[g.scale_off + 2 + 0]), row,
-                                  (keep ? sA : dump) + lane, keep ? BL_SA : 0, 1.0);
-    const double sb = bank_row<2>(x(1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
-                                  g.weight_off + g.n[0],
-                                  __double_as_longlong(c_grid[g.scale_off + 2 + 1]), row,
-                                  (keep ? sB : dump) + lane, keep ? BL_SB : 0, 1.0);
+    double sa, sb;
+    if constexpr (NFIX > 0) {
+        sa = bank_row_n<NFIX, 2>(x(0) * c_grid[g.scale_off + 0], g.node_off, g.weight_off,
+                                 __double_as_longlong(c_grid[g.scale_off + 2 + 0]), row,
+                                 (keep ? sA : dump) + lane, keep ? BL_SA : 0, 1.0);
+        sb = bank_row_n<NFIX, 2>(x(1) * c_grid[g.scale_off + 1], g.node_off + NFIX, g.weight_off + NFIX,
+                                 __double_as_longlong(c_grid[g.scale_off + 2 + 1]), row,
+                                 (keep ? sB : dump) + lane, keep ? BL_SB : 0, 1.0);
+    } else {
+        sa = bank_row<2>(x(0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
+                         __double_as_longlong(c_grid[g.scale_off + 2 + 0]), row,
+                         (keep ? sA : dump) + lane, keep ? BL_SA : 0, 1.0);
+        sb = bank_row<2>(x(1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
+                         g.weight_off + g.n[0],
+                         __double_as_longlong(c_grid[g.scale_off + 2 + 1]), row,
+                         (keep ? sB : dump) + lane, keep ? BL_SB : 0, 1.0);
+    }
     return bank_rcp(sa * sb);
 }
 
@@ -775,6 +799,7 @@ __device__ __forceinline__ void bl_stage_frags(double *sFrag, const double *__re
     for (int e = threadIdx.x; e < nfrag * BL_FRAG; e += BL_THREADS) sFrag[e] = __ldg(frags + e);
 }
 
+template <int NFIX>
 __global__ void __launch_bounds__(BL_THREADS)
 spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int *__restrict__ knot_off,
                      const double *__restrict__ knots, const double *__restrict__ frags,
@@ -821,7 +846,7 @@ spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int 
     double inv = 1.0;
     for (int p = 0; p < P; ++p) {
         if (!((present >> p) & 1u)) continue;
-        const double v = bl_rows(c_bgrid[p], [&](int d) { return __ldg(x + d); }, mine == p, sA, sB, lane);
+        const double v = bl_rows<NFIX>(c_bgrid[p], [&](int d) { return __ldg(x + d); }, mine == p, sA, sB, lane);
         if (mine == p) inv = v;
     }
     __syncwarp();
@@ -831,8 +856,13 @@ spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int 
         if ((present & (present - 1u)) == 0u) {
             const int p = __ffs(present) - 1;
 #pragma unroll 1
-            for (int t0 = 0; t0 < 4; t0 += 2)
-                bl_tiles2(c_bgrid[p], sFrag + (size_t)p * G * BL_FRAG, o0, no, t0, sA, sB, sOut, lane);
+            for (int t0 = 0; t0 < 4; t0 += 2) {
+                if constexpr (NFIX > 0)
+                    bl_tiles2_n<(NFIX + 3) / 4, (NFIX + 7) / 8>(sFrag + (size_t)p * G * BL_FRAG, o0, no, t0, sA,
+                                                                sB, sOut, lane);
+                else
+                    bl_tiles2(c_bgrid[p], sFrag + (size_t)p * G * BL_FRAG, o0, no, t0, sA, sB, sOut, lane);
+            }
         } else {
 #pragma unroll 1
             for (int t = 0; t < 4; ++t) {
@@ -860,6 +890,7 @@ spline2d_dmma_kernel(int G, int P, const int *__restrict__ num_knots, const int 
 // budget: with the four-tile routine ptxas keeps the bank reads on the uniform datapath at 80
 // registers and drops them at the unbounded 94; the same routine takes spline2d_dmma_kernel off the
 // uniform path at any budget, so that kernel multiplies tile by tile.  tools/check_sass.py)
+template <int NFIX>
 __global__ void __launch_bounds__(BL_THREADS, 6)
 slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ out_slide,
                      const int *__restrict__ row_out, const int *__restrict__ frag_off, int nfrag,
@@ -886,11 +917,15 @@ slider2d_dmma_kernel(int D, int S, int G, double pivot, const int *__restrict__ 
         const BankGrid &gr = c_bgrid[s];
         const int sg = gr.outputs;
         if (sg == 0) continue;
-        const double inv = bl_rows(gr, [&](int d) { return __ldg(x + gr.dims[d]); }, true, sA, sB, lane);
+        const double inv = bl_rows<NFIX>(gr, [&](int d) { return __ldg(x + gr.dims[d]); }, true, sA, sB, lane);
         __syncwarp();
         for (int o0 = 0; o0 < sg; o0 += BL_OUT) {
             const int no = sg - o0 < BL_OUT ? sg - o0 : BL_OUT;
-            bl_tiles4(gr, sFrag + (size_t)frag_off[s] * BL_FRAG, o0, no, sA, sB, sOut, lane);
+            if constexpr (NFIX > 0)
+                bl_tiles4_n<(NFIX + 3) / 4, (NFIX + 7) / 8>(sFrag + (size_t)frag_off[s] * BL_FRAG, o0, no, sA, sB,
+                                                            sOut, lane);
+            else
+                bl_tiles4(gr, sFrag + (size_t)frag_off[s] * BL_FRAG, o0, no, sA, sB, sOut, lane);
             __syncwarp();
             for (int k = 0; k < no; ++k) {
                 const int so = o0 + k;
@@ -1027,7 +1062,7 @@ __device__ __forceinline__ void bl3_tile_n(int n1, int n2, int fragstride, const
 // Measured on 15^3 (values): <1, 0> 2.03e9 q/s, <2, 3> 1.85e9, <2, 0> 1.92e9, <4, 0> 1.64e9 -- one
 // B-fragment load per two or four DMMAs and twice / four times the accumulator chains do not pay;
 // only <1, 0> is instantiated.
-template <int TL, int MINB>
+template <int TL, int MINB, int NFIX>
 __global__ void __launch_bounds__(BL3_THREADS, MINB)
 spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__restrict__ num_knots,
                      const int *__restrict__ knot_off, const double *__restrict__ knots,
@@ -1108,17 +1143,28 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
         const bool keep = mine == p;
         double row[GRID_NL];
         double *dump = sOut + BL_OUT * 32;
-        const double sa = bank_row<2>(__ldg(x + 0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
-                                      __double_as_longlong(c_grid[g.scale_off + 3 + 0]), row,
-                                      (keep ? sA : dump) + lane, keep ? BL3_SA : 0, 1.0);
-        const double sb = bank_row<2>(__ldg(x + 1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
-                                      g.weight_off + g.n[0],
-                                      __double_as_longlong(c_grid[g.scale_off + 3 + 1]), row,
-                                      (keep ? sB : dump) + lane, keep ? BL3_SA : 0, 1.0);
-        const double sc = bank_row<2>(__ldg(x + 2) * c_grid[g.scale_off + 2], g.n[2],
-                                      g.node_off + g.n[0] + g.n[1], g.weight_off + g.n[0] + g.n[1],
-                                      __double_as_longlong(c_grid[g.scale_off + 3 + 2]), row,
-                                      (keep ? sC : dump) + lane, keep ? BL3_SA : 0, 1.0);
+        double sa, sb, sc;
+        if constexpr (NFIX > 0) {
+            sa = bank_row_n<NFIX, 2>(__ldg(x + 0) * c_grid[g.scale_off + 0], g.node_off, g.weight_off,
+                                     __double_as_longlong(c_grid[g.scale_off + 3 + 0]), row,
+                                     (keep ? sA : dump) + lane, keep ? BL3_SA : 0, 1.0);
+            sb = bank_row_n<NFIX, 2>(__ldg(x + 1) * c_grid[g.scale_off + 1], g.node_off + NFIX,
+                                     g.weight_off + NFIX, __double_as_longlong(c_grid[g.scale_off + 3 + 1]),
+                                     row, (keep ? sB : dump) + lane, keep ? BL3_SA : 0, 1.0);
+            sc = bank_row_n<NFIX, 2>(__ldg(x + 2) * c_grid[g.scale_off + 2], g.node_off + 2 * NFIX,
+                                     g.weight_off + 2 * NFIX, __double_as_longlong(c_grid[g.scale_off + 3 + 2]),
+                                     row, (keep ? sC : dump) + lane, keep ? BL3_SA : 0, 1.0);
+        } else {
+            sa = bank_row<2>(__ldg(x + 0) * c_grid[g.scale_off + 0], g.n[0], g.node_off, g.weight_off,
+                             __double_as_longlong(c_grid[g.scale_off + 3 + 0]), row,
+                             (keep ? sA : dump) + lane, keep ? BL3_SA : 0, 1.0);
+            sb = bank_row<2>(__ldg(x + 1) * c_grid[g.scale_off + 1], g.n[1], g.node_off + g.n[0],
+                             g.weight_off + g.n[0], __double_as_longlong(c_grid[g.scale_off + 3 + 1]), row,
+                             (keep ? sB : dump) + lane, keep ? BL3_SA : 0, 1.0);
+            sc = bank_row<2>(__ldg(x + 2) * c_grid[g.scale_off + 2], g.n[2], g.node_off + g.n[0] + g.n[1],
+                             g.weight_off + g.n[0] + g.n[1], __double_as_longlong(c_grid[g.scale_off + 3 + 2]),
+                             row, (keep ? sC : dump) + lane, keep ? BL3_SA : 0, 1.0);
+        }
         const double v = bank_rcp(sa * sb * sc);
         if (keep) inv = v;
     }
@@ -1141,7 +1187,10 @@ spline3d_dmma_kernel(int G, int g0, int Gtot, int P, int KBmax, const int *__res
                 unsigned take = 0;
 #pragma unroll
                 for (int tl = 0; tl < TL; ++tl) take |= (prow[tl] == (unsigned)p ? 1u : 0u) << tl;
-                if (g.n[0] > 8)
+                if constexpr (NFIX > 0)
+                    bl3_tile_nm<(NFIX + 7) / 8, (NFIX + 3) / 4, TL>(NFIX, NFIX, fragstride, frag, o0, no, t0, sA, sB,
+                                                                    sC, sOut, lane, take);
+                else if (g.n[0] > 8)
                     bl3_tile_n<2, TL>(g.n[1], g.n[2], fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take);
                 else
                     bl3_tile_n<1, TL>(g.n[1], g.n[2], fragstride, frag, o0, no, t0, sA, sB, sC, sOut, lane, take);
@@ -1441,6 +1490,10 @@ extern "C" PCB_API int pcb_spline_plan_create(int dev, int D, const int32_t *num
             if (!pl->dmma2d_ok) cudaGetLastError();
         }
     }
+    pl->nfix = desc[0].n[0];
+    for (int p = 0; p < P; ++p)
+        for (int d = 0; d < D; ++d)
+            if (desc[p].n[d] != pl->nfix) pl->nfix = 0;
     // 3-D pieces of at most 16 nodes per dim: joint-K tensor-core path
     if (D == 3 && pl->bank_ok && P <= BANK_GRIDS && !getenv("PCB_NO_DMMA3D")) {
         bool fits = true;
@@ -1517,8 +1570,10 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
         void *dargs[] = {(void *)&pl->G, (void *)&pl->P, (void *)&pl->d_num_knots, (void *)&pl->d_knot_off,
                          (void *)&pl->d_knots, (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
                          (void *)&d_out, (void *)&d_piece};
-        return bank_launch(pl, part.id, part.h_bank, part.h_desc, (const void *)spline2d_dmma_kernel, dargs,
-                           dsm, N, static_cast<cudaStream_t>(stream), BL_THREADS);
+        const int nf = getenv("PCB_NO_NFIX") ? 0 : pl->nfix;  // every dim of every piece has nf nodes
+        const void *k2 = PCB_NFIX_KERNEL(nf, spline2d_dmma_kernel);
+        return bank_launch(pl, part.id, part.h_bank, part.h_desc, k2, dargs, dsm, N,
+                           static_cast<cudaStream_t>(stream), BL_THREADS);
     }
     if (pl->dmma3d_ok) {
         const SplinePlan::BankPart &part = pl->parts[0];
@@ -1536,7 +1591,17 @@ extern "C" PCB_API int pcb_spline_eval(void *plan, const double *d_points, int64
                              (void *)&pl->d_num_knots, (void *)&pl->d_knot_off, (void *)&pl->d_knots,
                              (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
                              (void *)&d_out, (void *)&piece, (void *)&qper};
-            const void *k3 = (const void *)spline3d_dmma_kernel<1, 0>;
+            // Fixed-node variants.  Uncapped, ptxas reads their bank operands per lane (LDC); a
+            // 56-register budget (minBlocks 3) brings the uniform datapath back but spills.  Measured
+            // on 15^3: generic 2.71e9 q/s, fixed + LDC 2.81e9, fixed + capped 2.64e9 -- the straight-line
+            // rows matter more than the operand path, so the variants stay uncapped.
+            const int nf3 = getenv("PCB_NO_NFIX") ? 0 : pl->nfix;
+            const void *k3 = nf3 == 8    ? (const void *)spline3d_dmma_kernel<1, 0, 8>
+                             : nf3 == 11 ? (const void *)spline3d_dmma_kernel<1, 0, 11>
+                             : nf3 == 12 ? (const void *)spline3d_dmma_kernel<1, 0, 12>
+                             : nf3 == 15 ? (const void *)spline3d_dmma_kernel<1, 0, 15>
+                             : nf3 == 16 ? (const void *)spline3d_dmma_kernel<1, 0, 16>
+                                         : (const void *)spline3d_dmma_kernel<1, 0, 0>;
             if (int rc = bank_launch(pl, part.id, part.h_bank, part.h_desc, k3, dargs, dsm, N,
                                      static_cast<cudaStream_t>(stream), threads, qper))
                 return rc;
@@ -1708,6 +1773,8 @@ extern "C" PCB_API int pcb_slider_plan_create(int dev, int D, int S, const int32
         std::vector<int> foff(S, 0);
         for (int sl = 0; sl < S; ++sl) {
             fits = fits && desc[sl].D == 2 && desc[sl].n[0] <= 16 && desc[sl].n[1] <= 16;
+            if (sl == 0) pl->nfix = desc[0].n[0];
+            if (desc[sl].n[0] != pl->nfix || desc[sl].n[1] != pl->nfix) pl->nfix = 0;
             foff[sl] = nfrag;
             nfrag += slide_G[sl];
         }
@@ -1745,8 +1812,9 @@ extern "C" PCB_API int pcb_slider_eval(void *plan, const double *d_points, int64
                          (void *)&pl->d_out_slide, (void *)&pl->d_row_out, (void *)&pl->d_frag_off,
                          (void *)&pl->nfrag, (void *)&pl->d_frags, (void *)&d_points, (void *)&N,
                          (void *)&d_out};
-        return bank_launch(pl, pl->plan_id, pl->h_bank, pl->h_desc, (const void *)slider2d_dmma_kernel, dargs,
-                           dsm, N, static_cast<cudaStream_t>(stream), BL_THREADS);
+        const int nf = getenv("PCB_NO_NFIX") ? 0 : pl->nfix;  // every dim of every slide has nf nodes
+        return bank_launch(pl, pl->plan_id, pl->h_bank, pl->h_desc, PCB_NFIX_KERNEL(nf, slider2d_dmma_kernel),
+                           dargs, dsm, N, static_cast<cudaStream_t>(stream), BL_THREADS);
     }
     if (pl->bank_ok) {
         const void *uk = BANK_KERNEL_TABLE(slider_bank_kernel, pl->GB, grid_pick_dm(pl->max_D));

@@ -316,3 +316,48 @@ def test_pcb_files_written_by_the_reference(case, tmp_path):
         # the loader rebuilds nodes, weights and differentiation matrices natively from the header
         # (no arrays of the reference object are shared): same 1e-12-class bound
         G.assert_close_scaled(got[:, g], ref, 1.0, f".pcb {kind} D={D} n={n_nodes} order {o}")
+
+
+# ------------------------------------------------------------------------------------------
+# kernels specialised on the node count of uniform grids (8, 11, 12, 15, 16 nodes in every dimension)
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [8, 11, 12, 15, 16, 9])
+@pytest.mark.parametrize("kind", ["spline2d", "spline3d", "slider"])
+def test_fixed_node_count_variants(kind, n, monkeypatch):
+    """Uniform grids take straight-line weight-row code (template argument = node count); 9 has no
+    variant and stays on the generic kernel.  Same arithmetic in the same order: the results must be
+    BIT-IDENTICAL to the generic kernel's (PCB_NO_NFIX), and within the usual bound of the reference."""
+    ref_mod = _ref()
+    from oracle import ref_objects as RO
+    from pychebyshev_b200 import dropin
+
+    rng = np.random.default_rng(BASE_SEED + 6000 + n)
+    if kind == "slider":
+        D = 4
+        domain = _domain(rng, D)
+        f = _smooth(rng, domain, terms=2)
+        obj = ref_mod.ChebyshevSlider(lambda x, _: float(f(*x)), D, domain, [n] * D, [[0, 2], [1, 3]],
+                                      [float(rng.uniform(lo, hi)) for lo, hi in domain])
+        obj.build(verbose=False)
+        pts = _queries(rng, domain, 3000)
+        orders = [[0] * D, [1, 0, 0, 0], [0, 0, 0, 2], [1, 1, 0, 0]]
+        ref = np.array([[obj.eval([float(v) for v in p], list(o)) for o in orders] for p in pts[:150]])
+        run = lambda: dropin.adopt(obj, cached=False).eval_batch_multi(pts, orders)  # noqa: E731
+    else:
+        D = 2 if kind == "spline2d" else 3
+        domain = _domain(rng, D)
+        knots = [[float(rng.uniform(domain[0][0] + 0.2 * (domain[0][1] - domain[0][0]),
+                                    domain[0][1] - 0.2 * (domain[0][1] - domain[0][0])))]] + [[]] * (D - 1)
+        obj = RO.spline_from_func(_smooth(rng, domain), domain, [n] * D, knots)
+        pts = _queries(rng, domain, 3000, knots=knots)
+        orders = [[0] * D, [1] + [0] * (D - 1), [0] * (D - 1) + [1]]
+        ref = np.stack([obj.eval_batch(pts[:150], o) for o in orders], axis=1)
+        run = lambda: dropin.adopt(obj, cached=False).eval_batch_multi(pts, orders)  # noqa: E731
+    fixed = run()
+    monkeypatch.setenv("PCB_NO_NFIX", "1")
+    generic = run()
+    assert np.array_equal(fixed, generic), f"{kind} n={n}: specialised and generic kernels differ"
+    for g, o in enumerate(orders):
+        G.assert_close_scaled(fixed[:150, g], ref[:, g], 1.0, f"{kind} n={n} order {o}",
+                              rel=2e-11 if kind == "slider" and any(o) else G.REL)

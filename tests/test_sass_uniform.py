@@ -28,7 +28,7 @@ def test_planner_default_kernels_read_the_bank_on_the_uniform_datapath():
     assert check_sass.regressions(rows) == []
     by = {r[0]: r for r in rows}
     # the tensor-core 2-D kernels really contain FP64 MMAs
-    assert by["spline2d_dmma_kernel"][5] >= 8 and by["slider2d_dmma_kernel"][5] >= 8
+    assert by["spline2d_dmma_kernel<0>"][5] >= 8 and by["slider2d_dmma_kernel<0>"][5] >= 8
     # every per-lane case is a known, documented one
     partial = {r[0] for r in rows if r[2] / max(1, r[1] + r[2]) > check_sass.MAX_LDC_SHARE}
     assert partial <= set(check_sass.KNOWN_PARTIAL) | {"ttc_fd_shared_kernel<2, 8, 256, 2>"}, partial

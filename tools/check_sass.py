@@ -33,14 +33,23 @@ MUST_BE_UNIFORM = (
     "spline_bank_kernel<1, 2>", "spline_bank_kernel<2, 2>", "spline_bank_kernel<2, 3>",
     "spline_bank_kernel<4, 2>", "spline_bank_kernel<4, 3>", "spline_bank_kernel<4, 4>",
     "slider_bank_kernel<1, 2>", "slider_bank_kernel<2, 2>", "slider_bank_kernel<4, 2>",
-    "spline2d_dmma_kernel", "slider2d_dmma_kernel", "spline3d_dmma_kernel<1, 0>",
+    "spline2d_dmma_kernel<0>", "spline2d_dmma_kernel<11>", "spline2d_dmma_kernel<15>",
+    "slider2d_dmma_kernel<0>", "spline3d_dmma_kernel<1, 0, 0>",
 )
 #: at most this share of a MUST_BE_UNIFORM kernel's bank reads may be per-lane (descriptor fields
 #: that feed per-lane predicates are legitimately read with LDC)
 MAX_LDC_SHARE = 0.15
 #: known partial cases (correct, slower), tracked so that NEW regressions stand out
 KNOWN_PARTIAL = ("ttc_gcoeff_kernel<2, 256>", "ttc_gstep_kernel<2, 256>", "spline_bank_kernel<1, 3>",
-                 "spline_bank_kernel<1, 4>", "slider_bank_kernel<1, 3>", "slider_bank_kernel<4, 4>")
+                 "spline_bank_kernel<1, 4>", "slider_bank_kernel<1, 3>", "slider_bank_kernel<4, 4>",
+                 # fixed-node-count variants: per-lane bank reads, but straight-line weight rows --
+                 # measured FASTER than the generic kernels on the uniform path (slider 11 x 11:
+                 # 5.24e9 against 4.74e9 q/s; 15^3 pieces: 2.81e9 against 2.71e9), and slower when a
+                 # register cap forces them back onto it
+                 "slider2d_dmma_kernel<8>", "slider2d_dmma_kernel<11>", "slider2d_dmma_kernel<12>",
+                 "slider2d_dmma_kernel<15>", "spline3d_dmma_kernel<1, 0, 8>",
+                 "spline3d_dmma_kernel<1, 0, 11>", "spline3d_dmma_kernel<1, 0, 15>",
+                 "spline3d_dmma_kernel<1, 0, 16>")
 
 
 def demangle_short(name):
